@@ -1,0 +1,88 @@
+"""ctypes binding of libl3d_b200.so (the C ABI declared in include/l3d_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a tensor is not a CUDA fp32 tensor the
+call raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libl3d_b200.so")
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+# name -> argtypes (all return int unless listed in _RESTYPE)
+_SIGNATURES = {
+    "l3d_abi_version": [],
+    "l3d_error_string": [_I],
+    "l3d_launch_count": [],
+    "l3d_debug_force_slow_path": [_I],
+    "l3d_knn_expansion": [_P, _I, _I, _I, _P, _P, _P],
+    "l3d_knn_expansion_host": [_P, _I, _I, _I, _P],
+    "l3d_graph_feature": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "l3d_graph_feature_grad": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "l3d_knn_point": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_knn_sqdist": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "l3d_pn2_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_pn2_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+}
+_RESTYPE = {
+    "l3d_error_string": ctypes.c_char_p,
+    "l3d_launch_count": ctypes.c_uint64,
+    "l3d_debug_force_slow_path": None,
+}
+
+
+def exported_symbols():
+    """Every symbol include/l3d_b200.h declares (checked by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "learning3d_b200: %s not found — build it with `make -C learning3d_b200/csrc` "
+                "(or __graft_entry__.build()).  There is no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, _I)
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().l3d_error_string(int(rc))
+        raise RuntimeError("learning3d_b200 %s failed: %s (code %d)" % (what, msg.decode(), rc))
+
+
+def stream():
+    return _P(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return _P(t.data_ptr()) if t is not None else _P(None)
+
+
+def require_cuda(t, name, dtype=torch.float32):
+    """The hot path is CUDA-only: never silently compute on the CPU."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("learning3d_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("learning3d_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def launch_count():
+    return int(lib().l3d_launch_count())

@@ -1,0 +1,166 @@
+// Shared device helpers for the learning3d_b200 kernels (sm_100a only).
+//
+// Everything in this tree is compiled with -fmad=false: a*b+c is NEVER contracted
+// behind our back.  Where the reference arithmetic is fused (MKL / cuBLAS K=3 GEMM,
+// nvcc-contracted pointnet2 kernels) the kernels call fmaf() explicitly, so the
+// rounding sequence of every distance is spelled out in the source and mirrored
+// one-to-one by oracle/l3d_oracle.c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define L3D_FULL_MASK 0xffffffffu
+
+// ---- error codes shared with include/l3d_b200.h ------------------------------------
+#define L3D_OK 0
+#define L3D_ERR_INVALID (-1)      // bad argument (null pointer, k > N, negative size ...)
+#define L3D_ERR_UNSUPPORTED (-2)  // shape outside what the kernels were built for
+
+#define L3D_LAUNCH_CHECK()                              \
+  do {                                                  \
+    cudaError_t e__ = cudaGetLastError();               \
+    if (e__ != cudaSuccess) return (int)e__;            \
+  } while (0)
+
+namespace l3d {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) ---------------------
+// A tensor-map (tiled) TMA box cannot express a 12-byte inner row, so point clouds are
+// moved as flat 16-byte-aligned byte ranges with cp.async.bulk and an mbarrier.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- ordering used by every selection kernel ---------------------------------------
+// "better" = larger key first; equal keys -> lower index first.  All kNN flavours map
+// their distance to a key whose LARGEST values are the nearest neighbours, so one
+// comparator serves knn(), knn_point(), pointnet2 knn / three_nn and Chamfer's argmin.
+__device__ __forceinline__ bool better(float av, uint32_t ai, float bv, uint32_t bi) {
+  return (av > bv) || (av == bv && ai < bi);
+}
+
+// Bitonic sort of 32*S (key, idx) pairs held S-per-lane; position p = s*32 + lane.
+// After the call position 0 holds the best pair, position 32*S-1 the worst.
+template <int S>
+__device__ __forceinline__ void warp_bitonic_sort(float (&v)[S], uint32_t (&ix)[S], int lane) {
+  constexpr int NTOT = 32 * S;
+#pragma unroll
+  for (int k2 = 2; k2 <= NTOT; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sp = s ^ js;
+          if (sp > s) {
+            const bool up = (((s * 32) & k2) == 0);  // lane bits < 32 <= k2 never matter here
+            const bool b = better(v[sp], ix[sp], v[s], ix[s]);
+            if (b == up) {
+              float tv = v[s]; v[s] = v[sp]; v[sp] = tv;
+              uint32_t ti = ix[s]; ix[s] = ix[sp]; ix[sp] = ti;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float pv = __shfl_xor_sync(L3D_FULL_MASK, v[s], j);
+          const uint32_t pi = __shfl_xor_sync(L3D_FULL_MASK, ix[s], j);
+          const int p = s * 32 + lane;
+          const bool up = ((p & k2) == 0);
+          const bool lower = ((lane & j) == 0);
+          const bool pb = better(pv, pi, v[s], ix[s]);
+          const bool take = (pb == (lower == up));
+          v[s] = take ? pv : v[s];
+          ix[s] = take ? pi : ix[s];
+        }
+      }
+    }
+  }
+}
+
+// Keys-only descending bitonic sort of 32*S floats (position p = s*32 + lane).
+template <int S>
+__device__ __forceinline__ void warp_bitonic_sort_keys(float (&v)[S], int lane) {
+  constexpr int NTOT = 32 * S;
+#pragma unroll
+  for (int k2 = 2; k2 <= NTOT; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int sp = s ^ js;
+          if (sp > s) {
+            const bool up = (((s * 32) & k2) == 0);
+            const float hi = fmaxf(v[s], v[sp]);
+            const float lo = fminf(v[s], v[sp]);
+            v[s] = up ? hi : lo;
+            v[sp] = up ? lo : hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float pv = __shfl_xor_sync(L3D_FULL_MASK, v[s], j);
+          const int p = s * 32 + lane;
+          const bool up = ((p & k2) == 0);
+          const bool lower = ((lane & j) == 0);
+          v[s] = (lower == up) ? fmaxf(v[s], pv) : fminf(v[s], pv);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(L3D_FULL_MASK, x, o);
+    if (lane >= o) x += y;
+  }
+  return x;
+}
+
+}  // namespace l3d

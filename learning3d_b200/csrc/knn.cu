@@ -1,0 +1,441 @@
+// Fused pairwise-distance + top-k selection (sm_100a).
+//
+// Replaces, without ever materialising the B x M x N distance matrix:
+//   knn()                       utils/model_common_utils.py:3-9      (MODE_EXPANSION_NEG)
+//   pointconv_util.knn_point()  utils/pointconv_util.py:107-118      (MODE_SQDIST_EXP)
+//   knn_point()                 utils/model_common_utils.py:84-100   (MODE_DIRECT_RN)
+//   pointnet2 knn / three_nn    utils/lib/src/interpolate_gpu.cu:9-57,81-124 (MODE_DIRECT_FMA)
+//
+// Design (one warp per query row):
+//   1. the candidate cloud of batch item b is bulk-copied (cp.async.bulk + mbarrier) into
+//      shared memory once per CTA and repacked to float4 (x, y, z, |p|^2);
+//   2. per row each lane evaluates 32 candidates per 1024-candidate tile into registers;
+//   3. lane-group maxima are bitonic-sorted across the warp: the k-th largest group maximum
+//      T0 is a proven lower bound of the k-th best key, so only keys >= T0 (about 1.5k of
+//      them) are compacted into a small shared-memory buffer;
+//   4. the survivors are bitonic-sorted by (key desc, index asc) and the first k written
+//      out with one coalesced store per row.
+//   A row whose survivors overflow the buffer (duplicate points, adversarial ties) is redone
+//   by an exact k-round arg-max scan, so the result is always the full (key, index) order.
+#include "common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+#include <math.h>
+
+namespace l3d {
+
+enum KnnMode {
+  MODE_EXPANSION_NEG = 0,  // key = ((-|c|^2) + 2 q.c) - |q|^2              (largest = nearest)
+  MODE_SQDIST_EXP = 1,     // key = -(((-2 q.c) + |q|^2) + |c|^2)
+  MODE_DIRECT_RN = 2,      // key = -((dx*dx + dy*dy) + dz*dz), each op rounded
+  MODE_DIRECT_FMA = 3      // key = -fma(dz,dz, fma(dy,dy, dx*dx))
+};
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_WARPS = KNN_THREADS / 32;
+constexpr int KNN_TILE = 1024;   // candidates per tile = 32 lanes x 32 registers
+constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
+
+struct KnnParams {
+  const float* cand;   // [B,3,N] (CAND_BCN) or [B,N,3]
+  const float* query;  // [B,M,3] or nullptr when SELF
+  void* out_idx;       // [B,M,k] int64 / int32
+  float* out_val;      // optional [B,M,k]
+  int B, N, M, k;
+  int idx64;      // 1 -> int64 indices, 0 -> int32
+  int val_xform;  // 0: key, 1: -key, 2: sqrt(-key)
+  int use_tma;    // alignment preconditions for cp.async.bulk hold
+  int force_slow;
+};
+
+template <int MODE>
+__device__ __forceinline__ float knn_key(const float4 q, const float4 c) {
+  if (MODE == MODE_EXPANSION_NEG) {
+    // torch.matmul K=3 accumulation: fma(z,z', fma(y,y', x*x'))  (model_common_utils.py:5)
+    const float dot = fmaf(q.z, c.z, fmaf(q.y, c.y, __fmul_rn(q.x, c.x)));
+    // pd = -xx - inner - xx^T, inner = -2*dot (exact): ((-|c|^2) + 2dot) - |q|^2   (:6-7)
+    return __fsub_rn(fmaf(2.0f, dot, -c.w), q.w);
+  } else if (MODE == MODE_SQDIST_EXP) {
+    const float dot = fmaf(q.z, c.z, fmaf(q.y, c.y, __fmul_rn(q.x, c.x)));
+    // dist = -2*matmul; dist += |src|^2; dist += |dst|^2   (pointconv_util.py:36-38)
+    const float v = __fadd_rn(fmaf(-2.0f, dot, q.w), c.w);
+    return -v;
+  } else if (MODE == MODE_DIRECT_RN) {
+    const float dx = __fsub_rn(c.x, q.x), dy = __fsub_rn(c.y, q.y), dz = __fsub_rn(c.z, q.z);
+    const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return -v;
+  } else {
+    const float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
+    const float v = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+    return -v;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 knn_pack(float x, float y, float z) {
+  float w = 0.0f;
+  if (MODE == MODE_EXPANSION_NEG || MODE == MODE_SQDIST_EXP)
+    w = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));  // sum(x**2)
+  return make_float4(x, y, z, w);
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 knn_padding() {
+  // a padded slot must evaluate to key = -inf for every finite query
+  if (MODE == MODE_EXPANSION_NEG || MODE == MODE_SQDIST_EXP)
+    return make_float4(0.f, 0.f, 0.f, INFINITY);
+  return make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+}
+
+__device__ __forceinline__ float knn_val_xform(float key, int xform) {
+  if (xform == 1) return -key;
+  if (xform == 2) return sqrtf(-key);
+  return key;
+}
+
+// Exact but O(k*N) selection: k rounds of "best pair strictly after the previous one".
+template <int MODE>
+__device__ __noinline__ void knn_row_slow(const KnnParams& p, const float4* __restrict__ packed,
+                                          const float4 q, long row, int lane) {
+  float pv = INFINITY;
+  uint32_t pi = 0;
+  bool first = true;
+  for (int r = 0; r < p.k; ++r) {
+    float bv = -INFINITY;
+    uint32_t bi = 0xffffffffu;
+    for (int j = lane; j < p.N; j += 32) {
+      const float d = knn_key<MODE>(q, packed[j]);
+      const bool after = first || better(pv, pi, d, (uint32_t)j);
+      if (after && better(d, (uint32_t)j, bv, bi)) { bv = d; bi = (uint32_t)j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(L3D_FULL_MASK, bv, o);
+      const uint32_t oi = __shfl_xor_sync(L3D_FULL_MASK, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      const long o = row * p.k + r;
+      if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)bi;
+      else reinterpret_cast<int*>(p.out_idx)[o] = (int)bi;
+      if (p.out_val) p.out_val[o] = knn_val_xform(bv, p.val_xform);
+    }
+    pv = bv; pi = bi; first = false;
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void knn_store(const KnnParams& p, long row, int lane,
+                                          const float (&v)[S], const uint32_t (&ix)[S]) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int pos = s * 32 + lane;
+    if (pos < p.k) {
+      const long o = row * p.k + pos;
+      if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)ix[s];
+      else reinterpret_cast<int*>(p.out_idx)[o] = (int)ix[s];
+      if (p.out_val) p.out_val[o] = knn_val_xform(v[s], p.val_xform);
+    }
+  }
+}
+
+// One query row, one warp.  KS = ceil(k/32) in {1,2,4}.
+template <int MODE, int KS>
+__device__ __forceinline__ void knn_row(const KnnParams& p, const float4* __restrict__ packed,
+                                        uint2* __restrict__ cbuf, const float4 q, long row,
+                                        int ntiles, int lane) {
+  constexpr int CAP = 64 * KS;   // survivors buffer (entries) per warp
+  constexpr int GE = 32 / KS;    // registers per lane group
+  const int k = p.k;
+
+  int base = 0;            // entries carried over from earlier tiles (the running top-k)
+  float kth = -INFINITY;   // key of the running k-th best
+  bool overflow = (p.force_slow != 0);
+
+  float rv[2 * KS];
+  uint32_t ri[2 * KS];
+
+  for (int t = 0; t < ntiles && !overflow; ++t) {
+    float d[32];
+    const float4* pt = packed + t * KNN_TILE + lane;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) d[e] = knn_key<MODE>(q, pt[e * 32]);
+
+    // k-th largest of the 32*KS lane-group maxima: at least k keys are >= T0
+    float gm[KS];
+#pragma unroll
+    for (int g = 0; g < KS; ++g) {
+      float m = d[g * GE];
+#pragma unroll
+      for (int e = 1; e < GE; ++e) m = fmaxf(m, d[g * GE + e]);
+      gm[g] = m;
+    }
+    warp_bitonic_sort_keys<KS>(gm, lane);
+    float t0 = gm[0];
+#pragma unroll
+    for (int g = 1; g < KS; ++g)
+      if (((k - 1) >> 5) == g) t0 = gm[g];
+    t0 = __shfl_sync(L3D_FULL_MASK, t0, (k - 1) & 31);
+    const float thr = fmaxf(t0, kth);
+
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) cnt += (d[e] >= thr) ? 1 : 0;
+    const int incl = warp_inclusive_scan(cnt, lane);
+    const int total = __shfl_sync(L3D_FULL_MASK, incl, 31);
+    if (base + total > CAP) { overflow = true; break; }
+
+    int off = base + incl - cnt;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (d[e] >= thr) {
+        cbuf[off] = make_uint2(__float_as_uint(d[e]), (uint32_t)(t * KNN_TILE + e * 32 + lane));
+        ++off;
+      }
+    }
+    __syncwarp();
+
+    const int n_in = base + total;
+    if (n_in <= 32 * KS) {
+      float v[KS];
+      uint32_t ix[KS];
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int pos = s * 32 + lane;
+        const uint2 c = cbuf[pos];   // buffer has CAP >= 32*KS entries: always in bounds
+        const bool ok = pos < n_in;
+        v[s] = ok ? __uint_as_float(c.x) : -INFINITY;
+        ix[s] = ok ? c.y : 0xffffffffu;
+      }
+      warp_bitonic_sort<KS>(v, ix, lane);
+#pragma unroll
+      for (int s = 0; s < KS; ++s) { rv[s] = v[s]; ri[s] = ix[s]; }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 2 * KS; ++s) {
+        const int pos = s * 32 + lane;
+        const uint2 c = cbuf[pos];
+        const bool ok = pos < n_in;
+        rv[s] = ok ? __uint_as_float(c.x) : -INFINITY;
+        ri[s] = ok ? c.y : 0xffffffffu;
+      }
+      warp_bitonic_sort<2 * KS>(rv, ri, lane);
+    }
+    __syncwarp();
+
+    if (t + 1 < ntiles) {
+      // carry the sorted top-k into the next tile as the first k buffer entries
+      float kv = rv[0];
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int pos = s * 32 + lane;
+        if (pos < k) cbuf[pos] = make_uint2(__float_as_uint(rv[s]), ri[s]);
+        if (((k - 1) >> 5) == s) kv = rv[s];
+      }
+      kth = __shfl_sync(L3D_FULL_MASK, kv, (k - 1) & 31);
+      base = k;
+      __syncwarp();
+    }
+  }
+
+  if (overflow) {
+    knn_row_slow<MODE>(p, packed, q, row, lane);
+  } else {
+    float v[KS];
+    uint32_t ix[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) { v[s] = rv[s]; ix[s] = ri[s]; }
+    knn_store<KS>(p, row, lane, v, ix);
+  }
+}
+
+// Dynamic shared memory layout (bytes):
+//   [0,16)                       mbarrier
+//   [16, 16 + 12*KNN_CHUNK)      raw staging chunk (3 * KNN_CHUNK floats)
+//   [.., + 16*NPAD)              packed candidates (float4), NPAD = N rounded up to KNN_TILE
+//   [.., + KNN_WARPS*CAP*8)      per-warp survivor buffers
+__host__ __device__ inline size_t knn_smem_bytes(int N, int KS) {
+  const size_t npad = (size_t)((N + KNN_TILE - 1) / KNN_TILE) * KNN_TILE;
+  return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad + (size_t)KNN_WARPS * 64 * KS * 8;
+}
+
+template <int MODE, int KS, bool SELF, bool CAND_BCN>
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* stage = reinterpret_cast<float*>(smem + 16);
+  float4* packed = reinterpret_cast<float4*>(smem + 16 + 12 * KNN_CHUNK);
+  const int N = p.N, M = p.M;
+  const int ntiles = (N + KNN_TILE - 1) / KNN_TILE;
+  const int npad = ntiles * KNN_TILE;
+  uint2* cbuf_all = reinterpret_cast<uint2*>(packed + npad);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint2* cbuf = cbuf_all + warp * (64 * KS);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  const long rows_total = (long)p.B * M;
+  const long r0 = rows_total * blockIdx.x / gridDim.x;
+  const long r1 = rows_total * (blockIdx.x + 1) / gridDim.x;
+
+  for (long seg = r0; seg < r1;) {
+    const int b = (int)(seg / M);
+    const long seg_end = min(r1, (long)(b + 1) * M);
+
+    // ---- stage candidate cloud b: bulk copy -> repack to (x,y,z,|p|^2) ---------------
+    const float* src = p.cand + (size_t)b * 3 * N;
+    for (int j0 = 0; j0 < N; j0 += KNN_CHUNK) {
+      const int cnt = min(KNN_CHUNK, N - j0);
+      if (p.use_tma) {
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar, (uint32_t)cnt * 12u);
+          if (CAND_BCN) {
+            bulk_g2s(stage, src + j0, (uint32_t)cnt * 4u, bar);
+            bulk_g2s(stage + KNN_CHUNK, src + N + j0, (uint32_t)cnt * 4u, bar);
+            bulk_g2s(stage + 2 * KNN_CHUNK, src + 2 * (size_t)N + j0, (uint32_t)cnt * 4u, bar);
+          } else {
+            bulk_g2s(stage, src + (size_t)j0 * 3, (uint32_t)cnt * 12u, bar);
+          }
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+      } else {
+        if (CAND_BCN) {
+          for (int i = tid; i < cnt; i += KNN_THREADS) {
+            stage[i] = src[j0 + i];
+            stage[KNN_CHUNK + i] = src[N + j0 + i];
+            stage[2 * KNN_CHUNK + i] = src[2 * (size_t)N + j0 + i];
+          }
+        } else {
+          for (int i = tid; i < cnt * 3; i += KNN_THREADS) stage[i] = src[(size_t)j0 * 3 + i];
+        }
+        __syncthreads();
+      }
+      for (int i = tid; i < cnt; i += KNN_THREADS) {
+        float x, y, z;
+        if (CAND_BCN) { x = stage[i]; y = stage[KNN_CHUNK + i]; z = stage[2 * KNN_CHUNK + i]; }
+        else { x = stage[3 * i]; y = stage[3 * i + 1]; z = stage[3 * i + 2]; }
+        packed[j0 + i] = knn_pack<MODE>(x, y, z);
+      }
+      __syncthreads();  // staging chunk may be overwritten; packed[] visible
+    }
+    for (int i = N + tid; i < npad; i += KNN_THREADS) packed[i] = knn_padding<MODE>();
+    __syncthreads();
+
+    // ---- rows of this segment, one warp each ---------------------------------------
+    for (long row = seg + warp; row < seg_end; row += KNN_WARPS) {
+      float4 q;
+      if (SELF) {
+        q = packed[(int)(row - (long)b * M)];
+      } else {
+        const float* qp = p.query + row * 3;
+        q = knn_pack<MODE>(qp[0], qp[1], qp[2]);
+      }
+      knn_row<MODE, KS>(p, packed, cbuf, q, row, ntiles, lane);
+    }
+    seg = seg_end;
+    __syncthreads();  // all warps done with packed[] before the next cloud is staged
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------
+static int g_force_slow = 0;
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MODE, int KS, bool SELF, bool CAND_BCN>
+static int knn_launch_t(KnnParams p, cudaStream_t stream) {
+  auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN>;
+  const size_t smem = knn_smem_bytes(p.N, KS);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, KNN_THREADS, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) return L3D_ERR_UNSUPPORTED;
+  if (occ > 4) occ = 4;
+  const long rows = (long)p.B * p.M;
+  long grid = (long)sm_count() * occ;          // persistent-style: every CTA resident at once
+  const long max_useful = (rows + KNN_WARPS - 1) / KNN_WARPS;
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, KNN_THREADS, smem, stream>>>(p);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+template <int MODE, bool SELF, bool CAND_BCN>
+static int knn_launch(KnnParams p, cudaStream_t stream) {
+  if (p.B < 0 || p.N < 1 || p.M < 0 || p.k < 1 || p.k > p.N) return L3D_ERR_INVALID;
+  if (!p.cand || !p.out_idx || (!SELF && !p.query)) return L3D_ERR_INVALID;
+  if (p.N > L3D_KNN_MAX_N || p.k > 128) return L3D_ERR_UNSUPPORTED;
+  if ((long)p.B * p.M == 0) return L3D_OK;
+  p.force_slow = g_force_slow;
+  p.use_tma = ((reinterpret_cast<uintptr_t>(p.cand) & 15u) == 0 && (p.N & 3) == 0) ? 1 : 0;
+  if (p.k <= 32) return knn_launch_t<MODE, 1, SELF, CAND_BCN>(p, stream);
+  if (p.k <= 64) return knn_launch_t<MODE, 2, SELF, CAND_BCN>(p, stream);
+  return knn_launch_t<MODE, 4, SELF, CAND_BCN>(p, stream);
+}
+
+}  // namespace l3d
+
+using namespace l3d;
+
+extern "C" void l3d_debug_force_slow_path(int on) { l3d::g_force_slow = on ? 1 : 0; }
+
+extern "C" int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
+                                 float* val_dev, void* stream) {
+  KnnParams p{};
+  p.cand = x_dev; p.query = nullptr; p.out_idx = idx_dev; p.out_val = val_dev;
+  p.B = B; p.N = N; p.M = N; p.k = k; p.idx64 = 1; p.val_xform = 0;
+  return knn_launch<MODE_EXPANSION_NEG, true, true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_knn_point(const float* data_dev, const float* query_dev, int B, int N, int M,
+                             int k, float* val_dev, int64_t* idx_dev, void* stream) {
+  KnnParams p{};
+  p.cand = data_dev; p.query = query_dev; p.out_idx = idx_dev; p.out_val = val_dev;
+  p.B = B; p.N = N; p.M = M; p.k = k; p.idx64 = 1; p.val_xform = 2;
+  return knn_launch<MODE_DIRECT_RN, false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_knn_sqdist(const float* xyz_dev, const float* new_xyz_dev, int B, int N, int S,
+                              int nsample, int64_t* idx_dev, void* stream) {
+  KnnParams p{};
+  p.cand = xyz_dev; p.query = new_xyz_dev; p.out_idx = idx_dev; p.out_val = nullptr;
+  p.B = B; p.N = N; p.M = S; p.k = nsample; p.idx64 = 1; p.val_xform = 1;
+  return knn_launch<MODE_SQDIST_EXP, false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_pn2_knn(int b, int n, int m, int k, const float* unknown_dev,
+                           const float* known_dev, float* dist2_dev, int32_t* idx_dev,
+                           void* stream) {
+  KnnParams p{};
+  p.cand = known_dev; p.query = unknown_dev; p.out_idx = idx_dev; p.out_val = dist2_dev;
+  p.B = b; p.N = m; p.M = n; p.k = k; p.idx64 = 0; p.val_xform = 1;
+  return knn_launch<MODE_DIRECT_FMA, false, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_pn2_three_nn(int b, int n, int m, const float* unknown_dev,
+                                const float* known_dev, float* dist2_dev, int32_t* idx_dev,
+                                void* stream) {
+  return l3d_pn2_knn(b, n, m, 3, unknown_dev, known_dev, dist2_dev, idx_dev, stream);
+}

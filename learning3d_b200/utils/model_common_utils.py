@@ -1,0 +1,93 @@
+"""Drop-in for learning3d/utils/model_common_utils.py — same names, arguments and error
+behaviour; every function launches hand-written sm_100a kernels through the C ABI.
+
+Reference: utils/model_common_utils.py:3-155.
+"""
+import torch
+
+from .. import _C
+
+
+def knn(x, k, add_one_to_k=False):
+    """utils/model_common_utils.py:3-9.  x [B,C,N] fp32 -> idx [B,N,k] int64, nearest first.
+
+    The B x N x N matrix of the reference (three 134 MB passes at B=32, N=1024) is never
+    materialised: distance evaluation and top-k selection are one fused kernel.
+    """
+    if add_one_to_k:
+        k = k + 1
+    x = _C.require_cuda(x, "x")
+    if x.dim() != 3:
+        raise ValueError("knn expects x of shape [B, C, N], got %s" % (tuple(x.shape),))
+    B, C, N = x.shape
+    if C != 3:
+        raise NotImplementedError(
+            "learning3d_b200.knn: C=%d — only the xyz graph (C == 3) is on the built hot path; "
+            "feature-space kNN is a 'next' row (SURVEY.md §8f)" % C)
+    if k > N:
+        # same failure class as torch.topk in the reference
+        raise RuntimeError("selected index k out of range")
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().l3d_knn_expansion(_C.ptr(x), B, N, k, _C.ptr(idx), _C.ptr(None),
+                                            _C.stream()), "knn")
+    return idx
+
+
+class _GraphFeature(torch.autograd.Function):
+    """cat(x[nbr], x[centre]) gather of get_graph_feature (:149-154) and its scatter backward."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        B, C, N = x.shape
+        k = idx.shape[-1]
+        out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _C.check(_C.lib().l3d_graph_feature(_C.ptr(x), _C.ptr(idx), B, C, N, k, _C.ptr(out),
+                                                _C.stream()), "get_graph_feature")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, N, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, C, N, k = ctx.dims
+        grad_out = grad_out.contiguous()
+        gx = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _C.check(_C.lib().l3d_graph_feature_grad(_C.ptr(grad_out), _C.ptr(idx), B, C, N, k,
+                                                     _C.ptr(gx), _C.stream()),
+                     "get_graph_feature backward")
+        return gx, None
+
+
+def get_graph_feature(x, k=20, device=None):
+    """utils/model_common_utils.py:132-155.  x [B,C,N(,1)] -> [B,2C,N,k] = cat(neighbour, centre).
+
+    `device` is accepted for signature compatibility; the result lives on x's device (the
+    reference's default picks 'cuda' whenever CUDA is available, :138-139).
+    """
+    x = x.view(*x.size()[:3])
+    x = _C.require_cuda(x, "x")
+    idx = knn(x, k=k)
+    return _GraphFeature.apply(x, idx)
+
+
+def knn_point(k, pos1, pos2):
+    """utils/model_common_utils.py:84-100.  pos1 [B,N,C] data, pos2 [B,M,C] queries ->
+    (sqrt(d2) [B,M,k], idx [B,M,k] int64), nearest first."""
+    pos1 = _C.require_cuda(pos1, "pos1")
+    pos2 = _C.require_cuda(pos2, "pos2")
+    B, N, C = pos1.shape
+    M = pos2.shape[1]
+    if C != 3 or pos2.shape[2] != 3:
+        raise NotImplementedError("learning3d_b200.knn_point: only C == 3 is built")
+    if k > N:
+        raise RuntimeError("selected index k out of range")
+    val = torch.empty((B, M, k), dtype=torch.float32, device=pos1.device)
+    idx = torch.empty((B, M, k), dtype=torch.int64, device=pos1.device)
+    with torch.cuda.device(pos1.device):
+        _C.check(_C.lib().l3d_knn_point(_C.ptr(pos1), _C.ptr(pos2), B, N, M, k, _C.ptr(val),
+                                        _C.ptr(idx), _C.stream()), "knn_point")
+    return val, idx

@@ -1,0 +1,69 @@
+"""Generate the golden fixtures in tests/golden/ by running the REAL reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+    python tests/golden/make_golden.py
+The reference is imported unmodified through a symlink package; `h5py` is
+stubbed because utils/transformer.py:4 imports it.  Inputs are seeded; outputs are what the
+reference's own CPU code returns.  The oracle (oracle/l3d_oracle.c) and the CUDA path are
+both tested against these files.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def import_reference():
+    tmp = tempfile.mkdtemp(prefix="l3dref_")
+    os.symlink(REF, os.path.join(tmp, "learning3d"))
+    sys.path.insert(0, tmp)
+    sys.modules["h5py"] = types.ModuleType("h5py")
+    import learning3d  # noqa: F401
+    return tmp
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: v.shape for k, v in arrays.items()})
+
+
+def gen_knn():
+    from learning3d.utils.model_common_utils import knn, get_graph_feature, knn_point, square_distance
+    from learning3d.utils import pointconv_util as pcu
+    torch.manual_seed(1234)
+    # knn / get_graph_feature (utils/model_common_utils.py:3-9,132-155)
+    for tag, (B, N, k) in {"a": (2, 256, 20), "b": (1, 300, 33), "c": (2, 128, 8)}.items():
+        while True:
+            x = torch.rand(B, 3, N)
+            idx = knn(x, k)
+            xx = (x ** 2).sum(1, keepdim=True)
+            pd = -xx - (-2 * torch.matmul(x.transpose(2, 1).contiguous(), x)) - xx.transpose(2, 1).contiguous()
+            top = torch.gather(pd, 2, idx)
+            # reject draws with exact ties inside the top-(k+1): topk's tie order is unspecified
+            top1 = pd.topk(k + 1, dim=-1)[0]
+            if (top1[..., 1:] == top1[..., :-1]).any():
+                continue
+            break
+        feat = get_graph_feature(x, k=k, device="cpu")
+        save("knn_" + tag, x=x.numpy(), idx=idx.numpy(), pd=top.numpy(), feat=feat.numpy(),
+             k=np.array(k))
+    # knn_point (:84-100), square_distance (:19-38), pointconv knn_point (pointconv_util.py:107-118)
+    data = torch.rand(2, 200, 3)
+    query = torch.rand(2, 90, 3)
+    val, idx = knn_point(12, data, query)
+    sd = square_distance(query, data)
+    pc_idx = pcu.knn_point(16, data, query)
+    save("knn_point", data=data.numpy(), query=query.numpy(), val=val.numpy(), idx=idx.numpy(),
+         sqdist=sd.numpy(), pc_idx=pc_idx.numpy())
+
+
+if __name__ == "__main__":
+    import_reference()
+    gen_knn()
