@@ -21,6 +21,7 @@
 #ifndef L3D_B200_H_
 #define L3D_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -107,6 +108,48 @@ int l3d_pn2_knn(int b, int n, int m, int k, const float* unknown_dev, const floa
 /* pointnet2_cuda.three_nn_wrapper (interpolate_gpu.cu:81-124): the k = 3 case. */
 int l3d_pn2_three_nn(int b, int n, int m, const float* unknown_dev, const float* known_dev,
                      float* dist2_dev, int32_t* idx_dev, void* stream);
+
+/* ---- Chamfer distance ---------------------------------------------------------------- */
+/*
+ * cd.forward_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2)
+ * (losses/cuda/chamfer_distance/chamfer_distance.cpp:27-40,180-185; kernel .cu:6-155; called from
+ * losses/cuda/chamfer_distance/chamfer_distance.py:34):
+ *   xyz1_dev [B,n,3], xyz2_dev [B,m,3] fp32 -> dist1_dev [B,n], dist2_dev [B,m] SQUARED nearest
+ *   distance, idx1_dev/idx2_dev int32 arg-min (lowest index on ties).
+ * Arithmetic is that of the reference's CPU nnsearch (chamfer_distance.cpp:59-87):
+ * d = (dx*dx + dy*dy) + dz*dz, no fma — results are bit-identical to cd.forward.
+ */
+int l3d_chamfer_forward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m,
+                        float* dist1_dev, float* dist2_dev, int32_t* idx1_dev, int32_t* idx2_dev,
+                        void* stream);
+/*
+ * cd.backward_cuda(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+ * (chamfer_distance.cpp:42-57; kernel .cu:158-209; called from chamfer_distance.py:57).
+ * Gather-form, deterministic, bit-identical to the CPU loops chamfer_distance.cpp:141-176;
+ * the outputs are fully overwritten (no memset needed, unlike .cu:201-202).
+ */
+int l3d_chamfer_backward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m,
+                         const float* graddist1_dev, const float* graddist2_dev,
+                         const int32_t* idx1_dev, const int32_t* idx2_dev, float* gradxyz1_dev,
+                         float* gradxyz2_dev, void* stream);
+/*
+ * Fused ChamferDistanceLoss (losses/chamfer_distance.py:34-51):
+ *   loss = (mean(sqrt(dist1)) + mean(sqrt(dist2))) / 2 in the same launch as the NN search.
+ * ws_dev: l3d_chamfer_ws_bytes(B,n,m) bytes of device scratch, zero-filled ONCE by the caller
+ * (the arrival counter resets itself); one workspace per concurrently running stream.
+ * loss_dev: device scalar.  dist/idx outputs as in l3d_chamfer_forward (kept for backward).
+ */
+size_t l3d_chamfer_ws_bytes(int B, int n, int m);
+int l3d_chamfer_loss_forward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m,
+                             float* dist1_dev, float* dist2_dev, int32_t* idx1_dev,
+                             int32_t* idx2_dev, float* loss_dev, void* ws_dev, void* stream);
+/* Backward of the fused loss: grad_loss_dev is the upstream scalar gradient ON THE DEVICE (no
+ * host sync); chain rule of /2, mean, sqrt and the Chamfer gather in one launch. */
+int l3d_chamfer_loss_backward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m,
+                              const float* dist1_dev, const float* dist2_dev,
+                              const int32_t* idx1_dev, const int32_t* idx2_dev,
+                              const float* grad_loss_dev, float* gradxyz1_dev, float* gradxyz2_dev,
+                              void* stream);
 
 #ifdef __cplusplus
 }

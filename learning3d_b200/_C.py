@@ -30,11 +30,17 @@ _SIGNATURES = {
     "l3d_knn_sqdist": [_P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_pn2_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_pn2_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "l3d_chamfer_ws_bytes": [_I, _I, _I],
+    "l3d_chamfer_loss_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "l3d_chamfer_loss_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPE = {
     "l3d_error_string": ctypes.c_char_p,
     "l3d_launch_count": ctypes.c_uint64,
     "l3d_debug_force_slow_path": None,
+    "l3d_chamfer_ws_bytes": ctypes.c_size_t,
 }
 
 

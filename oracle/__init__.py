@@ -128,3 +128,75 @@ def pn2_knn(k, unknown, known):
     idx, ip = _out((b, n, k), np.int32)
     lib().l3d_oracle_pn2_knn(b, n, m, k, up, kp, dp, ip)
     return d2, idx
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def chamfer_forward(xyz1, xyz2):
+    """cd.forward semantics: (dist1 [B,n], dist2 [B,m], idx1, idx2 int32)."""
+    xyz1, p1 = _f32(xyz1)
+    xyz2, p2 = _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    d1, dp1 = _out((b, n), np.float32)
+    d2, dp2 = _out((b, m), np.float32)
+    i1, ip1 = _out((b, n), np.int32)
+    i2, ip2 = _out((b, m), np.int32)
+    lib().l3d_oracle_chamfer_forward(p1, p2, b, n, m, dp1, dp2, ip1, ip2)
+    return d1, d2, i1, i2
+
+
+def chamfer_backward(xyz1, xyz2, gd1, gd2, idx1, idx2):
+    xyz1, p1 = _f32(xyz1)
+    xyz2, p2 = _f32(xyz2)
+    gd1, g1 = _f32(gd1)
+    gd2, g2 = _f32(gd2)
+    idx1, i1 = _i32(idx1)
+    idx2, i2 = _i32(idx2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    gx1, o1 = _out((b, n, 3), np.float32)
+    gx2, o2 = _out((b, m, 3), np.float32)
+    lib().l3d_oracle_chamfer_backward(p1, p2, b, n, m, g1, g2, i1, i2, o1, o2)
+    return gx1, gx2
+
+
+def chamfer_loss(xyz1, xyz2):
+    xyz1, p1 = _f32(xyz1)
+    xyz2, p2 = _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    f = lib().l3d_oracle_chamfer_loss
+    f.restype = ctypes.c_double
+    return float(f(p1, p2, b, n, m))
+
+
+def chamfer_loss_grads(xyz1, xyz2, grad_loss=1.0):
+    """Gradients of the loss above w.r.t. both clouds, float32 chain rule as torch applies it:
+    d/d dist = ((g/2)/numel) / (2*sqrt(dist)), then the native backward."""
+    d1, d2, i1, i2 = chamfer_forward(xyz1, xyz2)
+    g = np.float32(grad_loss) * np.float32(0.5)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gd1 = (g / np.float32(d1.size)) / (np.float32(2.0) * np.sqrt(d1))
+        gd2 = (g / np.float32(d2.size)) / (np.float32(2.0) * np.sqrt(d2))
+    return chamfer_backward(xyz1, xyz2, gd1.astype(np.float32), gd2.astype(np.float32), i1, i2)
+
+
+def ref_cd():
+    """The reference's own Chamfer extension compiled from /root/reference by oracle/build_ref.py
+    (module with forward/backward [CPU nnsearch] and forward_cuda/backward_cuda).  None when
+    oracle/_ref/cd_ref.so has not been built."""
+    path = os.path.join(_HERE, "_ref", "cd_ref.so")
+    if not os.path.exists(path):
+        return None
+    import importlib.machinery
+    import importlib.util
+    import torch  # noqa: F401  (libtorch symbols must be loaded first)
+    loader = importlib.machinery.ExtensionFileLoader("cd_ref", path)
+    spec = importlib.util.spec_from_loader("cd_ref", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod

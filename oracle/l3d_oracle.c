@@ -273,3 +273,95 @@ void l3d_oracle_pn2_knn(int b, int n, int m, int k, const float* unknown, const 
     free(keys); free(ids);
   }
 }
+
+/* ---- Chamfer ---------------------------------------------------------------------- */
+
+/* nnsearch: losses/cuda/chamfer_distance/chamfer_distance.cpp:59-87.  For every point of
+ * xyz1 [b,n,3] the squared distance to and index of its nearest point of xyz2 [b,m,3];
+ * products and sums in float, strict '<' (lowest index wins). */
+static void nnsearch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                     int32_t* idx) {
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < (long)b * n; ++r) {
+    const int i = (int)(r / n);
+    const float x1 = xyz1[r * 3 + 0], y1 = xyz1[r * 3 + 1], z1 = xyz1[r * 3 + 2];
+    double best = 0;
+    int besti = 0;
+    for (int k = 0; k < m; ++k) {
+      const float x2 = xyz2[((size_t)i * m + k) * 3 + 0] - x1;
+      const float y2 = xyz2[((size_t)i * m + k) * 3 + 1] - y1;
+      const float z2 = xyz2[((size_t)i * m + k) * 3 + 2] - z1;
+      const float df = x2 * x2 + y2 * y2 + z2 * z2; /* float expression, then widened (:77) */
+      const double d = df;
+      if (k == 0 || d < best) { best = d; besti = k; }
+    }
+    dist[r] = (float)best;
+    idx[r] = besti;
+  }
+}
+
+/* chamfer_distance_forward: chamfer_distance.cpp:90-111. */
+void l3d_oracle_chamfer_forward(const float* xyz1, const float* xyz2, int b, int n, int m,
+                                float* dist1, float* dist2, int32_t* idx1, int32_t* idx2) {
+  nnsearch(b, n, m, xyz1, xyz2, dist1, idx1);
+  nnsearch(b, m, n, xyz2, xyz1, dist2, idx2);
+}
+
+/* chamfer_distance_backward: chamfer_distance.cpp:114-177 (sequential, same statement order). */
+void l3d_oracle_chamfer_backward(const float* xyz1, const float* xyz2, int b, int n, int m,
+                                 const float* graddist1, const float* graddist2,
+                                 const int32_t* idx1, const int32_t* idx2, float* gradxyz1,
+                                 float* gradxyz2) {
+  for (long i = 0; i < (long)b * n * 3; ++i) gradxyz1[i] = 0;
+  for (long i = 0; i < (long)b * m * 3; ++i) gradxyz2[i] = 0;
+  for (int i = 0; i < b; ++i) {
+    for (int j = 0; j < n; ++j) {
+      const float x1 = xyz1[((size_t)i * n + j) * 3 + 0];
+      const float y1 = xyz1[((size_t)i * n + j) * 3 + 1];
+      const float z1 = xyz1[((size_t)i * n + j) * 3 + 2];
+      const int j2 = idx1[(size_t)i * n + j];
+      const float x2 = xyz2[((size_t)i * m + j2) * 3 + 0];
+      const float y2 = xyz2[((size_t)i * m + j2) * 3 + 1];
+      const float z2 = xyz2[((size_t)i * m + j2) * 3 + 2];
+      const float g = graddist1[(size_t)i * n + j] * 2;
+      gradxyz1[((size_t)i * n + j) * 3 + 0] += g * (x1 - x2);
+      gradxyz1[((size_t)i * n + j) * 3 + 1] += g * (y1 - y2);
+      gradxyz1[((size_t)i * n + j) * 3 + 2] += g * (z1 - z2);
+      gradxyz2[((size_t)i * m + j2) * 3 + 0] -= (g * (x1 - x2));
+      gradxyz2[((size_t)i * m + j2) * 3 + 1] -= (g * (y1 - y2));
+      gradxyz2[((size_t)i * m + j2) * 3 + 2] -= (g * (z1 - z2));
+    }
+    for (int j = 0; j < m; ++j) {
+      const float x1 = xyz2[((size_t)i * m + j) * 3 + 0];
+      const float y1 = xyz2[((size_t)i * m + j) * 3 + 1];
+      const float z1 = xyz2[((size_t)i * m + j) * 3 + 2];
+      const int j2 = idx2[(size_t)i * m + j];
+      const float x2 = xyz1[((size_t)i * n + j2) * 3 + 0];
+      const float y2 = xyz1[((size_t)i * n + j2) * 3 + 1];
+      const float z2 = xyz1[((size_t)i * n + j2) * 3 + 2];
+      const float g = graddist2[(size_t)i * m + j] * 2;
+      gradxyz2[((size_t)i * m + j) * 3 + 0] += g * (x1 - x2);
+      gradxyz2[((size_t)i * m + j) * 3 + 1] += g * (y1 - y2);
+      gradxyz2[((size_t)i * m + j) * 3 + 2] += g * (z1 - z2);
+      gradxyz1[((size_t)i * n + j2) * 3 + 0] -= (g * (x1 - x2));
+      gradxyz1[((size_t)i * n + j2) * 3 + 1] -= (g * (y1 - y2));
+      gradxyz1[((size_t)i * n + j2) * 3 + 2] -= (g * (z1 - z2));
+    }
+  }
+}
+
+/* chamfer_distance(): losses/chamfer_distance.py:34-40 on top of the native forward:
+ * (mean(sqrt(d1)) + mean(sqrt(d2))) / 2, accumulated in double (a checker, not a bit model
+ * of torch.mean's summation tree). */
+double l3d_oracle_chamfer_loss(const float* xyz1, const float* xyz2, int b, int n, int m) {
+  float* d1 = (float*)malloc(sizeof(float) * (size_t)b * n);
+  float* d2 = (float*)malloc(sizeof(float) * (size_t)b * m);
+  int32_t* i1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)b * n);
+  int32_t* i2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)b * m);
+  l3d_oracle_chamfer_forward(xyz1, xyz2, b, n, m, d1, d2, i1, i2);
+  double s1 = 0, s2 = 0;
+  for (long i = 0; i < (long)b * n; ++i) s1 += sqrt((double)d1[i]);
+  for (long i = 0; i < (long)b * m; ++i) s2 += sqrt((double)d2[i]);
+  free(d1); free(d2); free(i1); free(i2);
+  return 0.5 * (s1 / ((double)b * n) + s2 / ((double)b * m));
+}

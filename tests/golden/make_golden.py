@@ -64,6 +64,40 @@ def gen_knn():
          sqdist=sd.numpy(), pc_idx=pc_idx.numpy())
 
 
+def gen_chamfer():
+    """Chamfer: the reference's JIT extension (losses/cuda/chamfer_distance) run on CPU
+    (cd.forward / cd.backward == nnsearch) + the loss through losses/chamfer_distance.py with
+    autograd gradients.  Config C1 shape and a ragged n != m case."""
+    import learning3d.losses.cuda.chamfer_distance as ref_cd_pkg   # JIT-builds `cd`
+    from learning3d.losses.chamfer_distance import chamfer_distance, chamfer
+    torch.manual_seed(4321)
+    for tag, (B, n, m) in {"c1": (4, 1024, 1024), "ragged": (3, 200, 333)}.items():
+        a = torch.rand(B, n, 3, requires_grad=True)
+        b = torch.rand(B, m, 3, requires_grad=True)
+        d1, d2 = ref_cd_pkg.ChamferDistance()(a, b)
+        idx1 = torch.zeros(B, n, dtype=torch.int); idx2 = torch.zeros(B, m, dtype=torch.int)
+        dd1 = torch.zeros(B, n); dd2 = torch.zeros(B, m)
+        ref_cd_pkg.chamfer_distance.cd.forward(a.detach(), b.detach(), dd1, dd2, idx1, idx2)
+        assert torch.equal(dd1, d1) and torch.equal(dd2, d2)
+        g1 = torch.randn(B, n); g2 = torch.randn(B, m)
+        ga, gb = torch.autograd.grad([d1, d2], [a, b], [g1, g2])
+        loss = chamfer_distance(a, b)                     # native path (ext is importable here)
+        la, lb = torch.autograd.grad(loss, [a, b])
+        loss_torch = chamfer(a, b)                        # the pure-torch fallback, same value
+        save("chamfer_" + tag, xyz1=a.detach().numpy(), xyz2=b.detach().numpy(),
+             dist1=d1.detach().numpy(), dist2=d2.detach().numpy(), idx1=idx1.numpy(), idx2=idx2.numpy(),
+             graddist1=g1.numpy(), graddist2=g2.numpy(), gradxyz1=ga.numpy(), gradxyz2=gb.numpy(),
+             loss=loss.detach().numpy(), loss_torch=loss_torch.detach().numpy(),
+             loss_grad1=la.numpy(), loss_grad2=lb.numpy())
+
+
 if __name__ == "__main__":
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("TORCH_EXTENSIONS_DIR", tempfile.mkdtemp(prefix="l3dref_ext_"))
+    os.environ["CC"] = "/usr/bin/gcc"; os.environ["CXX"] = "/usr/bin/g++"
     import_reference()
-    gen_knn()
+    which = sys.argv[1:] or ["knn", "chamfer"]
+    if "knn" in which:
+        gen_knn()
+    if "chamfer" in which:
+        gen_chamfer()
