@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~10 s oracle timing")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs under ncu: no clock ramp, no CPU baseline, few secondary iterations")
     return ap.parse_args()
 
 
@@ -179,7 +181,7 @@ def run_ours(args, rank, local_rank, world):
     # clock ramp (untimed) + the W warm-up steps
     t0 = time.perf_counter()
     i = 0
-    while time.perf_counter() - t0 < 0.3:
+    while not args.profile and time.perf_counter() - t0 < 0.3:
         for _ in range(50):
             step(i); i += 1
         torch.cuda.synchronize()
@@ -210,7 +212,7 @@ def run_ours(args, rank, local_rank, world):
     sampler.join(timeout=1.0)
 
     # ---- end-to-end through the host-buffer C ABI (pinned host memory, copies inside) -----
-    e2e_steps = max(10, min(args.steps, 200))
+    e2e_steps = 3 if args.profile else max(10, min(args.steps, 200))
     hx = torch.rand(B, 3, N).pin_memory()
     hidx = torch.empty(B, N, k, dtype=torch.int64).pin_memory()
     for _ in range(3):
@@ -230,7 +232,7 @@ def run_ours(args, rank, local_rank, world):
 
     extra = {}
     try:
-        extra.update(chamfer_bench(torch, dev, dist_on, world))
+        extra.update(chamfer_bench(torch, dev, dist_on, world, 5 if args.profile else 200))
     except ImportError:
         pass
 
@@ -265,7 +267,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if extra:
             line["extra"] = extra
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
             line["cpu_baseline"] = cpu_baseline_port(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if dist_on:
@@ -281,7 +283,7 @@ def ncu_traffic():
         return None
 
 
-def chamfer_bench(torch, dev, dist_on, world):
+def chamfer_bench(torch, dev, dist_on, world, iters=200):
     """Secondary metric of BASELINE.json: Chamfer fwd+bwd clouds/s (config C1 shape per GPU and a
     B=32 batch), through the public ChamferDistanceLoss API."""
     from learning3d_b200.losses import ChamferDistanceLoss
@@ -290,11 +292,10 @@ def chamfer_bench(torch, dev, dist_on, world):
     for B in (4, 32):
         a = torch.rand(B, 1024, 3, device=dev, requires_grad=True)
         b = torch.rand(B, 1024, 3, device=dev, requires_grad=True)
-        for _ in range(10):
+        for _ in range(min(10, iters)):
             a.grad = b.grad = None
             crit(a, b).backward()
         torch.cuda.synchronize()
-        iters = 200
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):

@@ -151,6 +151,85 @@ int l3d_chamfer_loss_backward(const float* xyz1_dev, const float* xyz2_dev, int 
                               const float* grad_loss_dev, float* gradxyz1_dev, float* gradxyz2_dev,
                               void* stream);
 
+/* ---- pointnet2_cuda replacements (utils/lib/src/pointnet2_api.cpp:10-25) ------------------ */
+/* Same argument order, caller-allocated outputs and int32 indices as the reference wrappers. */
+
+/*
+ * ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx)   (ball_query.cpp / _gpu.cu:9-45,
+ * called from utils/lib/pointnet2_utils.py:247): for each of the m centres new_xyz_dev [b,m,3] the
+ * first nsample indices k (ascending) of xyz_dev [b,n,3] with d2 < radius*radius, padded with the
+ * first hit; a row with no hit is all 0 (the reference relies on the caller's .zero_(); here the
+ * kernel writes every slot).  idx_dev [b,m,nsample] int32.
+ */
+int l3d_pn2_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz_dev,
+                       const float* xyz_dev, int32_t* idx_dev, void* stream);
+/* group_points_wrapper(b,c,n,npoints,nsample,points,idx,out)  (group_points_gpu.cu:47-66;
+ * pointnet2_utils.py:202): out[b,c,p,s] = points[b,c,idx[b,p,s]]. */
+int l3d_pn2_group_points(int b, int c, int n, int npoints, int nsample, const float* points_dev,
+                         const int32_t* idx_dev, float* out_dev, void* stream);
+/* group_points_grad_wrapper (group_points_gpu.cu:8-25; pointnet2_utils.py:222): atomicAdd scatter
+ * into grad_points_dev [b,c,n], which the caller zero-fills (as the reference does). */
+int l3d_pn2_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                              const float* grad_out_dev, const int32_t* idx_dev,
+                              float* grad_points_dev, void* stream);
+/* gather_points_wrapper(b,c,n,npoints,points,idx,out)  (sampling_gpu.cu:8-24; pointnet2_utils.py:56):
+ * out[b,c,j] = points[b,c,idx[b,j]]. */
+int l3d_pn2_gather_points(int b, int c, int n, int npoints, const float* points_dev,
+                          const int32_t* idx_dev, float* out_dev, void* stream);
+/* gather_points_grad_wrapper (sampling_gpu.cu:46-63; pointnet2_utils.py:68). */
+int l3d_pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out_dev,
+                               const int32_t* idx_dev, float* grad_points_dev, void* stream);
+/* furthest_point_sampling_wrapper(b,n,m,points,temp,idx)  (sampling_gpu.cu:93-246;
+ * pointnet2_utils.py:28): temp_dev [b,n] must hold 1e10 on entry (caller-filled, as in the
+ * reference) and holds the final min-distances on return; idxs_dev [b,m] int32, idxs[:,0] = 0.
+ * Index-exact including the reference's tie rule.  n <= 8192. */
+int l3d_pn2_furthest_point_sampling(int b, int n, int m, const float* dataset_dev, float* temp_dev,
+                                    int32_t* idxs_dev, void* stream);
+/* three_interpolate_wrapper(b,c,m,n,points,idx,weight,out)  (interpolate_gpu.cu:149-169;
+ * pointnet2_utils.py:160) and its grad (interpolate_gpu.cu:192-214; pointnet2_utils.py:182). */
+int l3d_pn2_three_interpolate(int b, int c, int m, int n, const float* points_dev,
+                              const int32_t* idx_dev, const float* weight_dev, float* out_dev,
+                              void* stream);
+int l3d_pn2_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out_dev,
+                                   const int32_t* idx_dev, const float* weight_dev,
+                                   float* grad_points_dev, void* stream);
+
+/* ---- pure-torch grouping helpers ------------------------------------------------------------ */
+/*
+ * query_ball_point() in its three variants (utils/model_common_utils.py:102-130 [get_cnt],
+ * utils/pointconv_util.py:85-105, utils/ppfnet_util.py:96-131 [itself_indices]):
+ *   xyz_dev [B,N,3], new_xyz_dev [B,S,3]; radius2 = float32(radius**2) (the scalar the reference
+ *   compares against); keeps expansion-form d2 <= radius2, first nsample in index order, padded
+ *   with the first hit (or with itself_indices[b,s] when given, which is also excluded from the
+ *   hits); a row without hits is all N (what the reference's sort leaves).  group_idx_dev
+ *   [B,S,nsample] int64; cnt_dev optional [B,S] int64 = number of hits before truncation.
+ */
+int l3d_query_ball_point(const float* xyz_dev, const float* new_xyz_dev, int B, int N, int S,
+                         float radius2, int nsample, const int64_t* itself_indices_dev,
+                         int64_t* group_idx_dev, int64_t* cnt_dev, void* stream);
+/*
+ * farthest_point_sample() (model_common_utils.py:58-82, pointconv_util.py:60-83,
+ * ppfnet_util.py:71-93): start_dev optional [B] int64 first indices (NULL = start at 0, the
+ * pointconv / start_with_first_point variant); centroids_dev [B,npoint] int64.  N <= 8192.
+ */
+int l3d_farthest_point_sample(const float* xyz_dev, int B, int N, int npoint,
+                              const int64_t* start_dev, int64_t* centroids_dev, void* stream);
+/* square_distance(src, dst) (model_common_utils.py:19-38 and copies): out_dev [B,N,M]. */
+int l3d_square_distance(const float* src_dev, const float* dst_dev, int B, int N, int M,
+                        float* out_dev, void* stream);
+/* index_points(points, idx) (model_common_utils.py:40-56 and copies): points_dev [B,N,C],
+ * idx_dev [B,R] int64 (R = product of idx's trailing dims) -> out_dev [B,R,C]; and its backward
+ * (atomicAdd into a caller-zeroed grad_points_dev [B,N,C]). */
+int l3d_index_points(const float* points_dev, const int64_t* idx_dev, int B, int N, int64_t R, int C,
+                     float* out_dev, void* stream);
+int l3d_index_points_grad(const float* grad_out_dev, const int64_t* idx_dev, int B, int N, int64_t R,
+                          int C, float* grad_points_dev, void* stream);
+/* compute_density(xyz, bandwidth) (pointconv_util.py:199-209) as a fused row reduction:
+ * density[b,i] = mean_j( exp(-d2_ij / two_bw2) / norm ), two_bw2 = float32(2*bw*bw),
+ * norm = float32(2.5*bw). */
+int l3d_compute_density(const float* xyz_dev, int B, int N, float two_bw2, float norm,
+                        float* density_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

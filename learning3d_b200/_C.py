@@ -30,6 +30,20 @@ _SIGNATURES = {
     "l3d_knn_sqdist": [_P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_pn2_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_pn2_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_pn2_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
+    "l3d_pn2_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_pn2_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_pn2_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_pn2_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_pn2_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
+    "l3d_pn2_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_pn2_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_query_ball_point": [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P],
+    "l3d_farthest_point_sample": [_P, _I, _I, _I, _P, _P, _P],
+    "l3d_square_distance": [_P, _P, _I, _I, _I, _P, _P],
+    "l3d_index_points": [_P, _P, _I, _I, ctypes.c_int64, _I, _P, _P],
+    "l3d_index_points_grad": [_P, _P, _I, _I, ctypes.c_int64, _I, _P, _P],
+    "l3d_compute_density": [_P, _I, _I, _F, _F, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "l3d_chamfer_ws_bytes": [_I, _I, _I],

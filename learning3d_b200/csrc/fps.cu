@@ -1,0 +1,190 @@
+// Farthest point sampling (sm_100a).
+//
+// Replaces furthest_point_sampling_kernel (utils/lib/src/sampling_gpu.cu:93-209, K10) and the three
+// pure-torch loops farthest_point_sample (utils/model_common_utils.py:58-82,
+// utils/pointconv_util.py:60-83, utils/ppfnet_util.py:71-93: `npoint` iterations of ~6 tiny kernels).
+//
+// FPS is inherently sequential (npoint dependent rounds), so it is latency bound: one CTA per batch
+// item keeps every point and its running min-distance in REGISTERS for the whole run, and a round
+// costs one distance update per register, one shuffle arg-max, ONE __syncthreads (double-buffered
+// per-warp results) and a redundant per-warp final reduce — no global-memory traffic inside the loop
+// except the 12-byte read of the newly selected point (L1-resident).
+//
+// Selection semantics reproduced exactly (indices are bit-identical on tie-free AND tied inputs):
+//   mode 0 (pointnet2 CUDA): d = nvcc-contracted fma form; per-thread strict '>' over k = tid, tid+bs, ...;
+//           tree reduce keeps the LEFT (lower tid) entry on ties (sampling_gpu.cu:86-91,136-137):
+//           the winner among equal distances is the smallest (k mod bs, k), bs = the reference's
+//           block size 2^floor(log2 n) <= 1024 (cuda_utils.h:10-14);
+//   mode 1 (torch): d = (dx*dx + dy*dy) + dz*dz rounded; torch.max returns the first maximal index.
+#include "common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+#include <cmath>
+
+namespace l3d {
+
+constexpr int FPS_THREADS = 512;
+constexpr int FPS_WARPS = FPS_THREADS / 32;
+
+struct FpsParams {
+  const float* xyz;          // [B,N,3]
+  float* temp;               // optional [B,N] in/out running min distance (pointnet2 `temp`)
+  const long long* start;    // optional [B] start indices (torch random-start variants)
+  void* out;                 // [B,M] int32 / int64
+  int B, N, M;
+  int mode;                  // 0: pointnet2 CUDA, 1: torch
+  int idx64;
+  int ref_bs;                // the reference kernel's block size (tie rule of mode 0)
+  int ref_log2;              // log2(ref_bs)
+};
+
+__device__ __forceinline__ float fps_dist(int mode, float x, float y, float z, float cx, float cy,
+                                          float cz) {
+  const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+  if (mode == 0) return fmaf(dz, dz, fmaf(dx, dx, __fmul_rn(dy, dy)));           // sampling_gpu.cu:131
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // torch sum
+}
+
+// larger distance wins; equal distance -> smaller tie key wins
+__device__ __forceinline__ bool fps_better(float av, uint32_t at, float bv, uint32_t bt) {
+  return (av > bv) || (av == bv && at < bt);
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
+  __shared__ float s_v[2][FPS_WARPS];
+  __shared__ uint32_t s_t[2][FPS_WARPS];
+  __shared__ int s_k[2][FPS_WARPS];
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, M = p.M;
+  const float* xyz = p.xyz + (size_t)b * N * 3;
+
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+  uint32_t tk[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = tid + i * FPS_THREADS;
+    if (k < N) {
+      px[i] = xyz[k * 3]; py[i] = xyz[k * 3 + 1]; pz[i] = xyz[k * 3 + 2];
+      td[i] = p.temp ? p.temp[(size_t)b * N + k] : 1e10f;
+      // tie key: mode 1 orders by k.  Mode 0: the reference's smem tree (strides bs/2 .. 1, left
+      // entry kept on ties) prefers the thread whose id is smallest when read BIT-REVERSED over
+      // log2(bs) bits (stride 1 decides between even/odd tids last, i.e. bit 0 is most significant),
+      // and inside a thread the smallest k: key = (bitrev(k mod bs), k / bs).
+      if (p.mode == 0) {
+        const uint32_t r = (p.ref_log2 == 0) ? 0u : (__brev((uint32_t)(k % p.ref_bs)) >> (32 - p.ref_log2));
+        tk[i] = (r << 16) | (uint32_t)(k / p.ref_bs);
+      } else {
+        tk[i] = (uint32_t)k;
+      }
+    } else {
+      px[i] = py[i] = pz[i] = 0.f;
+      td[i] = -1.f;            // never selected (distances are >= 0)
+      tk[i] = 0xffffffffu;
+    }
+  }
+
+  int old = p.start ? (int)p.start[b] : 0;
+  if (tid == 0) {
+    if (p.idx64) reinterpret_cast<long long*>(p.out)[(size_t)b * M] = old;
+    else reinterpret_cast<int*>(p.out)[(size_t)b * M] = old;
+  }
+
+  for (int j = 1; j < M; ++j) {
+    const float cx = __ldg(xyz + old * 3), cy = __ldg(xyz + old * 3 + 1), cz = __ldg(xyz + old * 3 + 2);
+    float bv = -2.f;
+    uint32_t bt = 0xffffffffu;
+    int bk = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = tid + i * FPS_THREADS;
+      if (k < N) {
+        const float d = fps_dist(p.mode, px[i], py[i], pz[i], cx, cy, cz);
+        td[i] = fminf(d, td[i]);          // d2 = min(d, temp[k])  /  distance[mask] = dist[mask]
+      }
+      if (fps_better(td[i], tk[i], bv, bt)) { bv = td[i]; bt = tk[i]; bk = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(L3D_FULL_MASK, bv, o);
+      const uint32_t ot = __shfl_xor_sync(L3D_FULL_MASK, bt, o);
+      const int ok = __shfl_xor_sync(L3D_FULL_MASK, bk, o);
+      if (fps_better(ov, ot, bv, bt)) { bv = ov; bt = ot; bk = ok; }
+    }
+    const int buf = j & 1;
+    if (lane == 0) { s_v[buf][warp] = bv; s_t[buf][warp] = bt; s_k[buf][warp] = bk; }
+    __syncthreads();
+    // every warp reduces the FPS_WARPS partial winners redundantly: no second barrier
+    bv = (lane < FPS_WARPS) ? s_v[buf][lane] : -2.f;
+    bt = (lane < FPS_WARPS) ? s_t[buf][lane] : 0xffffffffu;
+    bk = (lane < FPS_WARPS) ? s_k[buf][lane] : 0;
+#pragma unroll
+    for (int o = FPS_WARPS / 2; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(L3D_FULL_MASK, bv, o);
+      const uint32_t ot = __shfl_xor_sync(L3D_FULL_MASK, bt, o);
+      const int ok = __shfl_xor_sync(L3D_FULL_MASK, bk, o);
+      if (fps_better(ov, ot, bv, bt)) { bv = ov; bt = ot; bk = ok; }
+    }
+    old = __shfl_sync(L3D_FULL_MASK, bk, 0);
+    if (tid == 0) {
+      if (p.idx64) reinterpret_cast<long long*>(p.out)[(size_t)b * M + j] = old;
+      else reinterpret_cast<int*>(p.out)[(size_t)b * M + j] = old;
+    }
+  }
+
+  if (p.temp) {
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = tid + i * FPS_THREADS;
+      if (k < N) p.temp[(size_t)b * N + k] = td[i];
+    }
+  }
+}
+
+static int fps_launch(FpsParams p, cudaStream_t s) {
+  if (!p.xyz || !p.out || p.B < 0 || p.N < 1 || p.M < 0) return L3D_ERR_INVALID;
+  if (p.B == 0 || p.M == 0) return L3D_OK;   // `if (m <= 0) return;` (sampling_gpu.cu:99)
+  if (p.N > 16 * FPS_THREADS || p.N > 65536) return L3D_ERR_UNSUPPORTED;
+  // the reference's launch width: opt_n_threads(n) = max(min(1 << int(log(n)/log(2)), 1024), 1)
+  const int pow_2 = (int)(std::log(static_cast<double>(p.N)) / std::log(2.0));
+  int bs = 1 << pow_2;
+  if (bs > 1024) bs = 1024;
+  if (bs < 1) bs = 1;
+  p.ref_bs = bs;
+  p.ref_log2 = 0;
+  while ((1 << p.ref_log2) < bs) ++p.ref_log2;
+  const int ppt = (p.N + FPS_THREADS - 1) / FPS_THREADS;
+  if (ppt <= 1) fps_kernel<1><<<p.B, FPS_THREADS, 0, s>>>(p);
+  else if (ppt <= 2) fps_kernel<2><<<p.B, FPS_THREADS, 0, s>>>(p);
+  else if (ppt <= 4) fps_kernel<4><<<p.B, FPS_THREADS, 0, s>>>(p);
+  else if (ppt <= 8) fps_kernel<8><<<p.B, FPS_THREADS, 0, s>>>(p);
+  else fps_kernel<16><<<p.B, FPS_THREADS, 0, s>>>(p);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+}  // namespace l3d
+
+using namespace l3d;
+
+extern "C" int l3d_pn2_furthest_point_sampling(int b, int n, int m, const float* dataset_dev,
+                                               float* temp_dev, int32_t* idxs_dev, void* stream) {
+  if (!temp_dev) return L3D_ERR_INVALID;
+  FpsParams p{};
+  p.xyz = dataset_dev; p.temp = temp_dev; p.start = nullptr; p.out = idxs_dev;
+  p.B = b; p.N = n; p.M = m; p.mode = 0; p.idx64 = 0;
+  return fps_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_farthest_point_sample(const float* xyz_dev, int B, int N, int npoint,
+                                         const int64_t* start_dev, int64_t* centroids_dev,
+                                         void* stream) {
+  FpsParams p{};
+  p.xyz = xyz_dev; p.temp = nullptr; p.start = (const long long*)start_dev; p.out = centroids_dev;
+  p.B = B; p.N = N; p.M = npoint; p.mode = 1; p.idx64 = 1;
+  return fps_launch(p, (cudaStream_t)stream);
+}

@@ -29,7 +29,7 @@ enum KnnMode {
   MODE_EXPANSION_NEG = 0,  // key = ((-|c|^2) + 2 q.c) - |q|^2              (largest = nearest)
   MODE_SQDIST_EXP = 1,     // key = -(((-2 q.c) + |q|^2) + |c|^2)
   MODE_DIRECT_RN = 2,      // key = -((dx*dx + dy*dy) + dz*dz), each op rounded
-  MODE_DIRECT_FMA = 3      // key = -fma(dz,dz, fma(dy,dy, dx*dx))
+  MODE_DIRECT_FMA = 3      // key = -fma(dz,dz, fma(dx,dx, dy*dy))  (nvcc's contraction, see below)
 };
 
 constexpr int KNN_THREADS = 256;
@@ -67,7 +67,10 @@ __device__ __forceinline__ float knn_key(const float4 q, const float4 c) {
     return -v;
   } else {
     const float dx = __fsub_rn(q.x, c.x), dy = __fsub_rn(q.y, c.y), dz = __fsub_rn(q.z, c.z);
-    const float v = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+    // nvcc (12.9, -O2, sm_100) compiles the reference's `dx*dx + dy*dy + dz*dz`
+    // (interpolate_gpu.cu:38,104) to FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.) — checked in the
+    // SASS of the reference file itself (oracle/README.md).
+    const float v = fmaf(dz, dz, fmaf(dx, dx, __fmul_rn(dy, dy)));
     return -v;
   }
 }

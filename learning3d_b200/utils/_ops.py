@@ -1,0 +1,118 @@
+"""Shared torch-facing wrappers over the C ABI for the pure-torch grouping helpers of the reference
+(utils/model_common_utils.py, utils/pointconv_util.py, utils/ppfnet_util.py).  The three reference
+modules carry near-identical copies of these functions; their drop-ins all route here."""
+import numpy as np
+import torch
+
+from .. import _C
+
+
+def _xyz(t, name):
+    t = _C.require_cuda(t, name)
+    if t.dim() != 3 or t.size(2) != 3:
+        raise NotImplementedError("learning3d_b200: %s must be [B, N, 3] (got %s); only xyz clouds are "
+                                  "on the built hot path" % (name, tuple(t.shape)))
+    return t
+
+
+def square_distance(src, dst):
+    """model_common_utils.py:19-38 — [B,N,3], [B,M,3] -> [B,N,M] expansion-form squared distance."""
+    src, dst = _xyz(src, "src"), _xyz(dst, "dst")
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _C.check(_C.lib().l3d_square_distance(_C.ptr(src), _C.ptr(dst), B, N, M, _C.ptr(out),
+                                              _C.stream()), "square_distance")
+    return out
+
+
+class _IndexPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        B, N, C = points.shape
+        R = idx.numel() // B if B > 0 else 0
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
+        with torch.cuda.device(points.device):
+            _C.check(_C.lib().l3d_index_points(_C.ptr(points), _C.ptr(idx), B, N, R, C, _C.ptr(out),
+                                               _C.stream()), "index_points")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, N, C, R)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, N, C, R = ctx.dims
+        grad_out = grad_out.contiguous()
+        gp = torch.zeros((B, N, C), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _C.check(_C.lib().l3d_index_points_grad(_C.ptr(grad_out), _C.ptr(idx), B, N, R, C,
+                                                    _C.ptr(gp), _C.stream()), "index_points backward")
+        return gp, None
+
+
+def index_points(points, idx):
+    """model_common_utils.py:40-56 — points [B,N,C], idx [B,S] or [B,S,K] int64 -> [B,S(,K),C]."""
+    points = _C.require_cuda(points, "points")
+    if not idx.is_cuda:
+        raise RuntimeError("learning3d_b200: idx must be a CUDA tensor (no CPU fallback)")
+    idx = idx.to(torch.int64).contiguous()
+    return _IndexPoints.apply(points, idx)
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """FPS with the torch reference semantics; `start` None -> index 0, else an int64 [B] tensor."""
+    xyz = _xyz(xyz, "xyz")
+    B, N, _ = xyz.shape
+    cent = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    if start is not None:
+        start = start.to(device=xyz.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(xyz.device):
+        _C.check(_C.lib().l3d_farthest_point_sample(_C.ptr(xyz), B, N, npoint, _C.ptr(start),
+                                                    _C.ptr(cent), _C.stream()), "farthest_point_sample")
+    return cent
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz, itself_indices=None, get_cnt=False):
+    xyz, new_xyz = _xyz(xyz, "xyz"), _xyz(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    idx = torch.empty((B, S, nsample), dtype=torch.int64, device=xyz.device)
+    cnt = torch.empty((B, S), dtype=torch.int64, device=xyz.device) if get_cnt else None
+    if itself_indices is not None:
+        itself_indices = itself_indices.to(device=xyz.device, dtype=torch.int64).contiguous()
+    # `sqrdists > radius ** 2`: python computes radius**2 in double, the comparison casts it to fp32
+    r2 = float(np.float32(radius ** 2))
+    with torch.cuda.device(xyz.device):
+        _C.check(_C.lib().l3d_query_ball_point(_C.ptr(xyz), _C.ptr(new_xyz), B, N, S, r2, nsample,
+                                               _C.ptr(itself_indices), _C.ptr(idx), _C.ptr(cnt),
+                                               _C.stream()), "query_ball_point")
+    return (idx, cnt) if get_cnt else idx
+
+
+def knn_sqdist(nsample, xyz, new_xyz):
+    """pointconv_util.knn_point (pointconv_util.py:107-118)."""
+    xyz, new_xyz = _xyz(xyz, "xyz"), _xyz(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    if nsample > N:
+        raise RuntimeError("selected index k out of range")
+    idx = torch.empty((B, S, nsample), dtype=torch.int64, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _C.check(_C.lib().l3d_knn_sqdist(_C.ptr(xyz), _C.ptr(new_xyz), B, N, S, nsample, _C.ptr(idx),
+                                         _C.stream()), "knn_point")
+    return idx
+
+
+def compute_density(xyz, bandwidth):
+    """pointconv_util.py:199-209 — fused row reduction, the N x N matrix is never materialised."""
+    xyz = _xyz(xyz, "xyz")
+    B, N, _ = xyz.shape
+    out = torch.empty((B, N), dtype=torch.float32, device=xyz.device)
+    two_bw2 = float(np.float32(2.0 * bandwidth * bandwidth))
+    norm = float(np.float32(2.5 * bandwidth))
+    with torch.cuda.device(xyz.device):
+        _C.check(_C.lib().l3d_compute_density(_C.ptr(xyz), B, N, two_bw2, norm, _C.ptr(out),
+                                              _C.stream()), "compute_density")
+    return out

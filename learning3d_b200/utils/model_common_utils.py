@@ -91,3 +91,41 @@ def knn_point(k, pos1, pos2):
         _C.check(_C.lib().l3d_knn_point(_C.ptr(pos1), _C.ptr(pos2), B, N, M, k, _C.ptr(val),
                                         _C.ptr(idx), _C.stream()), "knn_point")
     return val, idx
+
+
+# ---- the remaining helpers of utils/model_common_utils.py --------------------------------------
+from . import _ops  # noqa: E402
+import numpy as np  # noqa: E402
+
+
+def pc_normalize(pc):
+    """utils/model_common_utils.py:11-17 (numpy, host side; unchanged semantics)."""
+    centroid = np.mean(pc, axis=0)
+    pc = pc - centroid
+    m = np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+    return pc / m
+
+
+def square_distance(src, dst):
+    """utils/model_common_utils.py:19-38."""
+    return _ops.square_distance(src, dst)
+
+
+def index_points(points, idx):
+    """utils/model_common_utils.py:40-56."""
+    return _ops.index_points(points, idx)
+
+
+def farthest_point_sample(xyz, npoint, start_with_first_point=False):
+    """utils/model_common_utils.py:58-82.  The random start is drawn exactly as the reference draws
+    it (CPU generator, torch.randint(0, N, (B,))) so seeded runs pick the same points."""
+    B, N, _ = xyz.shape
+    farthest = torch.randint(0, N, (B,), dtype=torch.long)
+    if start_with_first_point:
+        farthest = farthest * 0
+    return _ops.farthest_point_sample(xyz, npoint, farthest)
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz, get_cnt=False):
+    """utils/model_common_utils.py:102-130."""
+    return _ops.query_ball_point(radius, nsample, xyz, new_xyz, None, get_cnt)

@@ -20,7 +20,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
 
+def _fresh(dst, srcs):
+    """True when dst exists and is newer than every source (skip the multi-minute rebuild)."""
+    if not os.path.exists(dst):
+        return False
+    t = os.path.getmtime(dst)
+    return all(os.path.getmtime(f) <= t for f in srcs)
+
+
 def build_chamfer():
+    src0 = os.path.join(REF, "losses", "cuda", "chamfer_distance")
+    if _fresh(os.path.join(OUT, "cd_ref.so"), [os.path.join(src0, "chamfer_distance.cpp"),
+                                               os.path.join(src0, "chamfer_distance.cu"), __file__]):
+        print("up to date: cd_ref.so")
+        return
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     os.environ["CC"] = "/usr/bin/gcc"
     os.environ["CXX"] = "/usr/bin/g++"
@@ -40,12 +53,40 @@ def build_chamfer():
     print("built", dst)
 
 
+def build_pointnet2():
+    """utils/lib/src/{ball_query,group_points,sampling,interpolate}_gpu.cu — the reference's CUDA
+    kernels and launchers, compiled in place with nvcc (their own setup.py needs THC, which torch
+    2.11 no longer ships; the .cu files only need torch's headers on the include path) together
+    with oracle/ref_shims/pn2_shim.cu (extern "C" wrappers, our own code)."""
+    import subprocess
+    import sysconfig
+    from torch.utils.cpp_extension import include_paths
+    src = os.path.join(REF, "utils", "lib", "src")
+    dst = os.path.join(OUT, "libpn2_ref.so")
+    srcs = [os.path.join(src, f + "_gpu.cu") for f in ("ball_query", "group_points", "sampling", "interpolate")]
+    srcs.append(os.path.join(HERE, "ref_shims", "pn2_shim.cu"))
+    if _fresh(dst, srcs + [__file__]):
+        print("up to date: libpn2_ref.so")
+        return
+    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+           "-shared", "-Xcompiler", "-fPIC", "-w", "-I" + src, "-I" + sysconfig.get_paths()["include"]]
+    cmd += ["-I" + p for p in include_paths()]
+    cmd += ["-o", dst] + srcs
+    env = dict(os.environ, CC="/usr/bin/gcc", CXX="/usr/bin/g++")
+    subprocess.run(cmd, check=True, env=env)
+    print("built", dst)
+
+
 def main():
     if not os.path.isdir(REF):
         print("no /root/reference here: keeping prebuilt oracle/_ref (if any)")
         return 0
     os.makedirs(OUT, exist_ok=True)
-    build_chamfer()
+    which = sys.argv[1:] or ["chamfer", "pointnet2"]
+    if "chamfer" in which:
+        build_chamfer()
+    if "pointnet2" in which:
+        build_pointnet2()
     return 0
 
 

@@ -243,9 +243,17 @@ void l3d_oracle_knn_point(const float* data, const float* query, int B, int N, i
   }
 }
 
+/* Squared distance as the pointnet2 CUDA kernels evaluate it.  The source expression is
+ * dx*dx + dy*dy + dz*dz (ball_query_gpu.cu:33, interpolate_gpu.cu:38,104, sampling_gpu.cu:131);
+ * nvcc 12.9 -O2 for sm_100 contracts it to FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.) — read off
+ * the SASS of the reference files themselves (oracle/README.md). */
+static inline float pn2_d2(float dx, float dy, float dz) {
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
 /* pointnet2 knn_kernel_fast / three_nn_kernel_fast: utils/lib/src/interpolate_gpu.cu:9-57,
  * 81-124 (CUDA-only reference; restated).  d = (ux-x)*(ux-x) + (uy-y)*(uy-y) + (uz-z)*(uz-z)
- * as nvcc contracts it: fma(dz,dz, fma(dy,dy, dx*dx)); insertion with strict '<' keeps the
+ * as nvcc contracts it (pn2_d2 above); insertion with strict '<' keeps the
  * earlier index first among equal distances; output ascending d2 + int32 idx.
  * unknown [b,n,3] queries, known [b,m,3] data. */
 void l3d_oracle_pn2_knn(int b, int n, int m, int k, const float* unknown, const float* known,
@@ -262,7 +270,7 @@ void l3d_oracle_pn2_knn(int b, int n, int m, int k, const float* unknown, const 
       for (int j = 0; j < m; ++j) {
         const float* p = known + ((size_t)bi * m + j) * 3;
         const float dx = u[0] - p[0], dy = u[1] - p[1], dz = u[2] - p[2];
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float d = pn2_d2(dx, dy, dz);
         topk_insert(keys, ids, &cnt, k, -d, j);
       }
       for (int t = 0; t < k; ++t) {

@@ -91,13 +91,50 @@ def gen_chamfer():
              loss_grad1=la.numpy(), loss_grad2=lb.numpy())
 
 
+def gen_group():
+    """Pure-torch grouping helpers on CPU: the three query_ball_point / farthest_point_sample variants,
+    index_points, compute_density, and the sample_and_group compositions."""
+    from learning3d.utils import model_common_utils as mcu
+    from learning3d.utils import pointconv_util as pcu
+    from learning3d.utils import ppfnet_util as ppu
+    torch.manual_seed(99)
+    xyz = torch.rand(2, 300, 3)
+    new_xyz = xyz[:, ::3].contiguous()                       # queries are a subset (100 per item)
+    normals = torch.nn.functional.normalize(torch.randn(2, 300, 3), dim=-1)
+    feats = torch.randn(2, 300, 5)
+    out = {"xyz": xyz, "new_xyz": new_xyz, "normals": normals, "feats": feats}
+    idx, cnt = mcu.query_ball_point(0.25, 16, xyz, new_xyz, get_cnt=True)
+    out["qbp_idx"], out["qbp_cnt"] = idx, cnt
+    out["qbp_small_r"] = pcu.query_ball_point(0.05, 8, xyz, new_xyz)       # many rows with 1 hit
+    itself = torch.arange(0, 300, 3)[None].repeat(2, 1)
+    out["qbp_itself"] = ppu.query_ball_point(0.25, 16, xyz, new_xyz, itself)
+    out["fps_first"] = mcu.farthest_point_sample(xyz, 64, start_with_first_point=True)
+    out["fps_pointconv"] = pcu.farthest_point_sample(xyz, 50)
+    torch.manual_seed(7)
+    out["fps_random_seed7"] = mcu.farthest_point_sample(xyz, 40)
+    torch.manual_seed(8)
+    out["fps_ppf_seed8"] = ppu.farthest_point_sample(xyz, 40)
+    out["index_points"] = mcu.index_points(feats, idx)
+    out["density"] = pcu.compute_density(xyz, 0.1)
+    nx, npts, gnorm, gidx = pcu.sample_and_group(32, 8, xyz, feats)
+    out["pc_sg_new_xyz"], out["pc_sg_new_points"], out["pc_sg_idx"] = nx, npts, gidx
+    torch.manual_seed(11)
+    res, gxyz, fidx = ppu.sample_and_group_multi(20, 0.3, 12, xyz, normals, returnfps=True)
+    out["ppf_xyz"], out["ppf_dxyz"], out["ppf_ppf"], out["ppf_fps"] = res["xyz"], res["dxyz"], res["ppf"], fidx
+    res_all = ppu.sample_and_group_multi(-1, 0.3, 12, xyz, normals)
+    out["ppf_all_ppf"] = res_all["ppf"]
+    save("group", **{k: v.numpy() for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     os.environ.setdefault("TORCH_EXTENSIONS_DIR", tempfile.mkdtemp(prefix="l3dref_ext_"))
     os.environ["CC"] = "/usr/bin/gcc"; os.environ["CXX"] = "/usr/bin/g++"
     import_reference()
-    which = sys.argv[1:] or ["knn", "chamfer"]
+    which = sys.argv[1:] or ["knn", "chamfer", "group"]
     if "knn" in which:
         gen_knn()
     if "chamfer" in which:
         gen_chamfer()
+    if "group" in which:
+        gen_group()
