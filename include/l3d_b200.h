@@ -230,6 +230,44 @@ int l3d_index_points_grad(const float* grad_out_dev, const int64_t* idx_dev, int
 int l3d_compute_density(const float* xyz_dev, int B, int N, float two_bw2, float norm,
                         float* density_dev, void* stream);
 
+/* ---- approximate EMD (losses/cuda/emd_torch) ---------------------------------------------- */
+/*
+ * emd_forward(xyz1, xyz2) -> [cost, match]   (pkg/include/emd.h:25-33, pkg/src/cuda/emd.cu:8-43;
+ * kernels approxmatch emd.cuh:6-185 + matchcost emd.cuh:201-244; called from
+ * pkg/layer/emd_loss_layer.py:10):  xyz1_dev [B,n,3], xyz2_dev [B,m,3] -> cost_dev [B] and,
+ * optionally (NULL to skip), match_dev [B,n,m] in the reference's memory order
+ * match[b*n*m + l*n + k] (l indexes xyz2, k indexes xyz1; emd.cuh:158).
+ * The reference allocates its outputs and `temp`; here the caller passes them, plus ws_dev with
+ * l3d_emd_forward_ws_bytes(B,n,m) bytes of scratch (no initialisation needed).  No
+ * cudaDeviceSynchronize (the reference syncs inside, emd.cuh:197).  fp32; agreement with the
+ * sequential restatement ~1e-6 relative.
+ */
+size_t l3d_emd_forward_ws_bytes(int B, int n, int m);
+int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m, float* cost_dev,
+                    float* match_dev, void* ws_dev, void* stream);
+/*
+ * emd_backward(xyz1, xyz2, match) -> [grad_xyz1, grad_xyz2]   (pkg/include/emd.h:35-46,
+ * emd.cu:45-70; kernels matchcostgrad1/2 emd.cuh:258-323): gradients of cost with the matching
+ * held constant.  ws_dev: l3d_emd_backward_ws_bytes(B,n,m) bytes.  Deterministic (fixed-order
+ * partial sums instead of one serial thread per point).
+ */
+size_t l3d_emd_backward_ws_bytes(int B, int n, int m);
+int l3d_emd_backward(const float* xyz1_dev, const float* xyz2_dev, const float* match_dev, int B, int n,
+                     int m, float* grad1_dev, float* grad2_dev, void* ws_dev, void* stream);
+
+/* ---- DCP SVD head tail (utils/svd.py:29-58) -------------------------------------------------- */
+/*
+ * Given H = src_centered * src_corr_centered^T (H_dev [B,3,3]) and the two means (src_mean_dev,
+ * corr_mean_dev [B,3]): R = V U^T of the SVD of H with the determinant fix of svd.py:40-45, and
+ * t = -R*mean(src) + mean(src_corr) (:58).  Replaces the per-item torch.svd / torch.det loop and
+ * its host synchronisation.  R_dev [B,3,3], t_dev [B,3].
+ */
+int l3d_kabsch3x3_batched(const float* H_dev, const float* src_mean_dev, const float* corr_mean_dev,
+                          int B, float* R_dev, float* t_dev, void* stream);
+/* Same, fused with the centring and the H reduction: src_dev, src_corr_dev [B,3,N] (svd.py:29-33). */
+int l3d_svd_head_tail(const float* src_dev, const float* src_corr_dev, int B, int N, float* R_dev,
+                      float* t_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,12 @@ _SIGNATURES = {
     "l3d_index_points": [_P, _P, _I, _I, ctypes.c_int64, _I, _P, _P],
     "l3d_index_points_grad": [_P, _P, _I, _I, ctypes.c_int64, _I, _P, _P],
     "l3d_compute_density": [_P, _I, _I, _F, _F, _P, _P],
+    "l3d_emd_forward_ws_bytes": [_I, _I, _I],
+    "l3d_emd_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_emd_backward_ws_bytes": [_I, _I, _I],
+    "l3d_emd_backward": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "l3d_kabsch3x3_batched": [_P, _P, _P, _I, _P, _P, _P],
+    "l3d_svd_head_tail": [_P, _P, _I, _I, _P, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "l3d_chamfer_ws_bytes": [_I, _I, _I],
@@ -55,6 +61,8 @@ _RESTYPE = {
     "l3d_launch_count": ctypes.c_uint64,
     "l3d_debug_force_slow_path": None,
     "l3d_chamfer_ws_bytes": ctypes.c_size_t,
+    "l3d_emd_forward_ws_bytes": ctypes.c_size_t,
+    "l3d_emd_backward_ws_bytes": ctypes.c_size_t,
 }
 
 

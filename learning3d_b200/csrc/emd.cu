@@ -1,0 +1,410 @@
+// Approximate Earth Mover's Distance (approxmatch / matchcost / matchcostgrad), sm_100a.
+//
+// Replaces losses/cuda/emd_torch/pkg/include/cuda/emd.cuh (K3 :6-185, K4 :201-244, K5 :301-323,
+// K6 :258-299) and pkg/src/cuda/emd.cu:8-70.
+//
+// The reference runs ONE 512-thread CTA per batch item (8 of 148 SMs at B=8) through 30 full
+// N x M exp-sweeps and read-modify-writes the N x M `match` matrix in global memory on each of
+// its 10 levels.  Here every sweep is a grid-wide "weighted row sweep"
+//     S[r] = sum_c exp(level * |p_r - q_c|^2) * v[c]
+// spread over all SMs (a warp owns 4 rows, columns staged in shared memory), and the three
+// per-level sweeps are algebraically regrouped so that `match` is never touched inside the loop:
+//   (1) ratioL[k] = remainL[k] / (1e-9 + S(level; v = remainR))                 emd.cuh:32-60
+//   (2) sumr[l]   = remainR[l] * S^T(level; v = ratioL); ratioR/remainR update   emd.cuh:80-116
+//   (3) suml[k]   = ratioL[k] * S(level; v = ratioR); remainL update             emd.cuh:135-168
+// (3) of level j and (1) of level j+1 sweep the same rows over the same columns and are fused
+// (two exponentials per pair, one pass).  The per-level (ratioL, ratioR) vectors are kept (10*(n+m)
+// floats per item) and one final pass rebuilds match = sum_j exp(level_j d2) ratioL_j[k] ratioR_j[l]
+// with coalesced stores (written once instead of 10 read-modify-writes) fused with the matchcost
+// reduction.  20 sweep launches + 1 final launch; MUFU(ex2)-bound.
+// fp32 throughout, ex2.approx like the reference's __expf; results agree with the sequential
+// restatement to ~1e-6 relative (summation order differs), inside the 1e-5 contract.
+#include "common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+namespace l3d {
+
+constexpr int EMD_THREADS = 256;
+constexpr int EMD_WARPS = EMD_THREADS / 32;
+constexpr int EMD_R = 4;                         // rows per warp
+constexpr int EMD_ROWS_PER_CTA = EMD_WARPS * EMD_R;
+constexpr int EMD_CHUNK = 1024;                  // columns staged per chunk
+constexpr int EMD_LEVELS = 10;                   // j = 7 .. -2 (emd.cuh:27)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ inline float emd_level(int it) {
+  // level = -4^j for j = 7..-1, and 0 at j = -2   (emd.cuh:28-31)
+  if (it == EMD_LEVELS - 1) return 0.f;
+  float v = 1.f;
+  const int j = 7 - it;
+  if (j >= 0) { for (int i = 0; i < j; ++i) v *= 4.f; }
+  else { for (int i = 0; i < -j; ++i) v *= 0.25f; }
+  return -v;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float emd_d2(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = bx - ax, dy = by - ay, dz = bz - az;
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+enum { EMD_PH1 = 1, EMD_PH2 = 2, EMD_PH3_PH1 = 3 };
+
+struct EmdSweepParams {
+  const float* rows;    // [B,nr,3] row cloud
+  const float* cols;    // [B,nc,3] column cloud
+  int B, nr, nc;
+  int phase;
+  float lvlA, lvlB;     // level*log2(e) for sweep A (and B when fused)
+  const float* vA;      // [B,nc] column weights of sweep A
+  const float* vB;      // [B,nc] column weights of sweep B (fused only)
+  // per-row state (all [B,nr])
+  float* remain;        // remainL (ph1, ph3) or remainR (ph2)
+  const float* ratio_in;   // ratioL of the finishing level (ph3)
+  float* ratio_out;        // ratioL (ph1 / fused) or ratioR (ph2) of the level being computed
+  float multi;             // initial remain value when `init` (multiL)
+  int init;                // ph1 of the first level: remain = multi
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(const EmdSweepParams p) {
+  __shared__ float4 s_col[EMD_CHUNK];
+  __shared__ float s_vb[FUSED ? EMD_CHUNK : 1];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * EMD_ROWS_PER_CTA + warp * EMD_R;
+  const float* rows = p.rows + (size_t)b * p.nr * 3;
+  const float* cols = p.cols + (size_t)b * p.nc * 3;
+
+  float rx[EMD_R], ry[EMD_R], rz[EMD_R], sa[EMD_R], sb[EMD_R];
+#pragma unroll
+  for (int i = 0; i < EMD_R; ++i) {
+    const int r = min(r0 + i, p.nr - 1);
+    rx[i] = rows[r * 3]; ry[i] = rows[r * 3 + 1]; rz[i] = rows[r * 3 + 2];
+    sa[i] = 0.f; sb[i] = 0.f;
+  }
+  for (int c0 = 0; c0 < p.nc; c0 += EMD_CHUNK) {
+    const int cn = min(EMD_CHUNK, p.nc - c0);
+    __syncthreads();
+    for (int c = tid; c < cn; c += EMD_THREADS) {
+      const float* q = cols + (size_t)(c0 + c) * 3;
+      s_col[c] = make_float4(q[0], q[1], q[2], p.vA[(size_t)b * p.nc + c0 + c]);
+      if (FUSED) s_vb[c] = p.vB[(size_t)b * p.nc + c0 + c];
+    }
+    __syncthreads();
+    for (int c = lane; c < cn; c += 32) {
+      const float4 q = s_col[c];
+      const float vb = FUSED ? s_vb[c] : 0.f;
+#pragma unroll
+      for (int i = 0; i < EMD_R; ++i) {
+        const float d2 = emd_d2(rx[i], ry[i], rz[i], q.x, q.y, q.z);
+        sa[i] = fmaf(ex2_approx(p.lvlA * d2), q.w, sa[i]);
+        if (FUSED) sb[i] = fmaf(ex2_approx(p.lvlB * d2), vb, sb[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < EMD_R; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa[i] += __shfl_xor_sync(L3D_FULL_MASK, sa[i], o);
+      if (FUSED) sb[i] += __shfl_xor_sync(L3D_FULL_MASK, sb[i], o);
+    }
+  }
+  if (lane < EMD_R) {
+    float S = sa[0], S2 = sb[0];
+#pragma unroll
+    for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = sa[i]; S2 = sb[i]; }
+    const int r = r0 + lane;
+    if (r < p.nr) {
+      const size_t o = (size_t)b * p.nr + r;
+      if (p.phase == EMD_PH1) {
+        const float rem = p.init ? p.multi : p.remain[o];
+        if (p.init) p.remain[o] = rem;
+        p.ratio_out[o] = rem / (1e-9f + S);                       // emd.cuh:40,60
+      } else if (p.phase == EMD_PH2) {
+        const float rem = p.remain[o];
+        const float sumr = S * rem;                                 // emd.cuh:110
+        const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+        p.ratio_out[o] = consumption * rem;
+        p.remain[o] = fmaxf(0.0f, rem - sumr);
+      } else {
+        // finish level j: remainL = max(0, remainL - ratioL_j * S_j)   (emd.cuh:157-168) ...
+        const float rem = fmaxf(0.0f, p.remain[o] - p.ratio_in[o] * S);
+        p.remain[o] = rem;
+        // ... and start level j+1: ratioL_{j+1} = remainL / (1e-9 + S_{j+1})
+        p.ratio_out[o] = rem / (1e-9f + S2);
+      }
+    }
+  }
+}
+
+// Final pass: match[b, l, k] (reference index l*n + k, emd.cuh:158) = sum_j exp(level_j d2)
+// ratioL_j[k] ratioR_j[l]; cost[b] = sum match * |x1_k - x2_l|   (emd.cuh:201-244).
+// One warp per l (row of match), lanes over k: coalesced stores.  Deterministic two-level cost sum.
+struct EmdFinalParams {
+  const float* xyz1; const float* xyz2;   // [B,n,3], [B,m,3]
+  const float* ratioL;                    // [LEVELS,B,n]
+  const float* ratioR;                    // [LEVELS,B,m]
+  float* match;                           // optional [B,m*n]
+  float* partial;                         // [B, gridDim.x]
+  float* cost;                            // [B]
+  unsigned int* ticket;                   // [B] self-resetting
+  int B, n, m;
+  float lvl[EMD_LEVELS];
+};
+
+__global__ void __launch_bounds__(EMD_THREADS) emd_final_kernel(const EmdFinalParams p) {
+  __shared__ float red[EMD_WARPS];
+  __shared__ bool is_last;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = blockIdx.x * EMD_WARPS + warp;
+  const float* x1 = p.xyz1 + (size_t)b * p.n * 3;
+  float acc = 0.f;
+  if (l < p.m) {
+    const float* q = p.xyz2 + ((size_t)b * p.m + l) * 3;
+    const float qx = q[0], qy = q[1], qz = q[2];
+    float rr[EMD_LEVELS];
+#pragma unroll
+    for (int j = 0; j < EMD_LEVELS; ++j) rr[j] = p.ratioR[((size_t)j * p.B + b) * p.m + l];
+    for (int k = lane; k < p.n; k += 32) {
+      const float d2 = emd_d2(x1[k * 3], x1[k * 3 + 1], x1[k * 3 + 2], qx, qy, qz);
+      float mt = 0.f;
+#pragma unroll
+      for (int j = 0; j < EMD_LEVELS; ++j) {
+        const float e = (j == EMD_LEVELS - 1) ? 1.0f : ex2_approx(p.lvl[j] * d2);
+        const float rl = p.ratioL[((size_t)j * p.B + b) * p.n + k];
+        mt += e * rl * rr[j];                                       // match += w   (emd.cuh:157-158)
+      }
+      if (p.match) p.match[(size_t)b * p.n * p.m + (size_t)l * p.n + k] = mt;
+      acc = fmaf(sqrtf(d2), mt, acc);                               // emd.cuh:225-226
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(L3D_FULL_MASK, acc, o);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < EMD_WARPS; ++w) s += red[w];
+    p.partial[(size_t)b * gridDim.x + blockIdx.x] = s;
+    __threadfence();
+    is_last = (atomicAdd(p.ticket + b, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float a = 0.f;
+    for (unsigned i = tid; i < gridDim.x; i += EMD_THREADS) a += __ldcg(p.partial + (size_t)b * gridDim.x + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(L3D_FULL_MASK, a, o);
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < EMD_WARPS; ++w) s += red[w];
+      p.cost[b] = s;
+      p.ticket[b] = 0u;
+    }
+  }
+}
+
+// ---- gradients (match held constant) -------------------------------------------------------
+// grad2[l] = sum_k match[l,k] (x2_l - x1_k) / max(|.|, 1e-10)   (emd.cuh:258-299): warp per l.
+__global__ void __launch_bounds__(EMD_THREADS) emd_grad2_kernel(const float* __restrict__ xyz1,
+                                                                const float* __restrict__ xyz2,
+                                                                const float* __restrict__ match,
+                                                                int n, int m, float* __restrict__ grad2) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int l = blockIdx.x * EMD_WARPS + (threadIdx.x >> 5);
+  if (l >= m) return;
+  const float* x1 = xyz1 + (size_t)b * n * 3;
+  const float* q = xyz2 + ((size_t)b * m + l) * 3;
+  const float* mrow = match + (size_t)b * n * m + (size_t)l * n;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int k = lane; k < n; k += 32) {
+    const float dx = qx - x1[k * 3], dy = qy - x1[k * 3 + 1], dz = qz - x1[k * 3 + 2];
+    const float d = mrow[k] * rsqrtf(fmaxf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)), 1e-20f));
+    gx = fmaf(dx, d, gx); gy = fmaf(dy, d, gy); gz = fmaf(dz, d, gz);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gx += __shfl_xor_sync(L3D_FULL_MASK, gx, o);
+    gy += __shfl_xor_sync(L3D_FULL_MASK, gy, o);
+    gz += __shfl_xor_sync(L3D_FULL_MASK, gz, o);
+  }
+  if (lane == 0) {
+    float* g = grad2 + ((size_t)b * m + l) * 3;
+    g[0] = gx; g[1] = gy; g[2] = gz;
+  }
+}
+
+// grad1[k] = sum_l match[l,k] (x1_k - x2_l) / max(|.|, 1e-10)   (emd.cuh:301-323): thread per k,
+// coalesced along k, rows l split in `slices` (grid.y) whose partial sums are combined in a fixed
+// order by emd_grad1_reduce_kernel (deterministic).
+__global__ void __launch_bounds__(EMD_THREADS) emd_grad1_partial_kernel(
+    const float* __restrict__ xyz1, const float* __restrict__ xyz2, const float* __restrict__ match,
+    int n, int m, int slices, float* __restrict__ partial /*[B,slices,n,3]*/) {
+  const int b = blockIdx.z, sl = blockIdx.y;
+  const int k = blockIdx.x * EMD_THREADS + threadIdx.x;
+  const int l0 = (int)((long)m * sl / slices), l1 = (int)((long)m * (sl + 1) / slices);
+  if (k >= n) return;
+  const float* p1 = xyz1 + ((size_t)b * n + k) * 3;
+  const float px = p1[0], py = p1[1], pz = p1[2];
+  const float* x2 = xyz2 + (size_t)b * m * 3;
+  const float* mb = match + (size_t)b * n * m;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int l = l0; l < l1; ++l) {
+    const float dx = px - __ldg(x2 + l * 3), dy = py - __ldg(x2 + l * 3 + 1), dz = pz - __ldg(x2 + l * 3 + 2);
+    const float d = mb[(size_t)l * n + k] * rsqrtf(fmaxf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)), 1e-20f));
+    gx = fmaf(dx, d, gx); gy = fmaf(dy, d, gy); gz = fmaf(dz, d, gz);
+  }
+  float* o = partial + (((size_t)b * slices + sl) * n + k) * 3;
+  o[0] = gx; o[1] = gy; o[2] = gz;
+}
+__global__ void __launch_bounds__(256) emd_grad1_reduce_kernel(const float* __restrict__ partial, int B,
+                                                               int n, int slices, float* __restrict__ grad1) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * n * 3) return;
+  const int b = (int)(t / ((long)n * 3));
+  const long r = t - (long)b * n * 3;
+  float s = 0.f;
+  for (int sl = 0; sl < slices; ++sl) s += partial[((size_t)b * slices + sl) * n * 3 + r];
+  grad1[t] = s;
+}
+
+__global__ void emd_fill_kernel(float* dst, long n, float v, unsigned int* ticket, int B) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+  if (i < B) ticket[i] = 0u;
+}
+
+static int emd_slices(int B, int n, int m) {
+  int s = 1;
+  const long ctas = (long)B * ((n + EMD_THREADS - 1) / EMD_THREADS);
+  while (s < 32 && ctas * s < 296 && m / (s * 2) >= 16) s *= 2;
+  return s;
+}
+
+}  // namespace l3d
+
+using namespace l3d;
+
+// workspace layout (floats): remainL[B,n] remainR[B,m] ratioL[LEVELS,B,n] ratioR[LEVELS,B,m]
+//                            partial[B*gx] | ticket[B] (uint)
+static size_t emd_fwd_ws_floats(int B, int n, int m) {
+  const size_t gx = (size_t)(m + EMD_WARPS - 1) / EMD_WARPS;
+  return (size_t)B * n + (size_t)B * m + (size_t)B * EMD_LEVELS * ((size_t)n + m) + (size_t)B * gx + (size_t)B;
+}
+extern "C" size_t l3d_emd_forward_ws_bytes(int B, int n, int m) {
+  if (B < 1 || n < 1 || m < 1) return 0;
+  return sizeof(float) * emd_fwd_ws_floats(B, n, m);
+}
+extern "C" size_t l3d_emd_backward_ws_bytes(int B, int n, int m) {
+  if (B < 1 || n < 1 || m < 1) return 0;
+  return sizeof(float) * (size_t)B * emd_slices(B, n, m) * n * 3;
+}
+
+extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int B, int n, int m,
+                               float* cost_dev, float* match_dev, void* ws_dev, void* stream) {
+  if (!xyz1_dev || !xyz2_dev || !cost_dev || !ws_dev || B < 0 || n < 1 || m < 1 || B > 65535)
+    return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(ws_dev);
+  float* remainL = ws;
+  float* remainR = remainL + (size_t)B * n;
+  float* ratioL = remainR + (size_t)B * m;
+  float* ratioR = ratioL + (size_t)B * EMD_LEVELS * n;
+  const unsigned gx_final = (unsigned)((m + EMD_WARPS - 1) / EMD_WARPS);
+  float* partial = ratioR + (size_t)B * EMD_LEVELS * m;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + (size_t)B * gx_final);
+
+  // multiL / multiR with the reference's INTEGER division (emd.cuh:10-16)
+  const float multiL = (n >= m) ? 1.f : (float)(m / n);
+  const float multiR = (n >= m) ? (float)(n / m) : 1.f;
+  {
+    // remainR = multiR (emd.cuh:24-25) and zero the arrival tickets
+    const long tot = (long)B * m;
+    emd_fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(remainR, tot, multiR, ticket, B);
+    count_launch();
+    L3D_LAUNCH_CHECK();
+  }
+  const dim3 gridL((n + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
+  const dim3 gridR((m + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
+  EmdFinalParams fp{};
+  for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it) * LOG2E;
+
+  for (int it = 0; it < EMD_LEVELS; ++it) {
+    if (it == 0) {
+      EmdSweepParams p{};
+      p.rows = xyz1_dev; p.cols = xyz2_dev; p.B = B; p.nr = n; p.nc = m; p.phase = EMD_PH1;
+      p.lvlA = fp.lvl[0]; p.vA = remainR; p.remain = remainL; p.ratio_out = ratioL;  // level 0 slot
+      p.multi = multiL; p.init = 1;
+      emd_sweep_kernel<false><<<gridL, EMD_THREADS, 0, s>>>(p);
+      count_launch();
+      L3D_LAUNCH_CHECK();
+    }
+    {
+      EmdSweepParams p{};
+      p.rows = xyz2_dev; p.cols = xyz1_dev; p.B = B; p.nr = m; p.nc = n; p.phase = EMD_PH2;
+      p.lvlA = fp.lvl[it]; p.vA = ratioL + (size_t)it * B * n; p.remain = remainR;
+      p.ratio_out = ratioR + (size_t)it * B * m;
+      emd_sweep_kernel<false><<<gridR, EMD_THREADS, 0, s>>>(p);
+      count_launch();
+      L3D_LAUNCH_CHECK();
+    }
+    if (it + 1 < EMD_LEVELS) {
+      EmdSweepParams p{};
+      p.rows = xyz1_dev; p.cols = xyz2_dev; p.B = B; p.nr = n; p.nc = m; p.phase = EMD_PH3_PH1;
+      p.lvlA = fp.lvl[it]; p.vA = ratioR + (size_t)it * B * m;
+      p.lvlB = fp.lvl[it + 1]; p.vB = remainR;
+      p.remain = remainL; p.ratio_in = ratioL + (size_t)it * B * n;
+      p.ratio_out = ratioL + (size_t)(it + 1) * B * n;
+      emd_sweep_kernel<true><<<gridL, EMD_THREADS, 0, s>>>(p);
+      count_launch();
+      L3D_LAUNCH_CHECK();
+    }
+  }
+  fp.xyz1 = xyz1_dev; fp.xyz2 = xyz2_dev; fp.ratioL = ratioL; fp.ratioR = ratioR;
+  fp.match = match_dev; fp.partial = partial; fp.cost = cost_dev; fp.ticket = ticket;
+  fp.B = B; fp.n = n; fp.m = m;
+  emd_final_kernel<<<dim3(gx_final, B), EMD_THREADS, 0, s>>>(fp);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+extern "C" int l3d_emd_backward(const float* xyz1_dev, const float* xyz2_dev, const float* match_dev,
+                                int B, int n, int m, float* grad1_dev, float* grad2_dev, void* ws_dev,
+                                void* stream) {
+  if (!xyz1_dev || !xyz2_dev || !match_dev || !grad1_dev || !grad2_dev || !ws_dev || B < 0 || n < 1 ||
+      m < 1 || B > 65535)
+    return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  emd_grad2_kernel<<<dim3((m + EMD_WARPS - 1) / EMD_WARPS, B), EMD_THREADS, 0, s>>>(
+      xyz1_dev, xyz2_dev, match_dev, n, m, grad2_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  const int slices = emd_slices(B, n, m);
+  float* partial = reinterpret_cast<float*>(ws_dev);
+  emd_grad1_partial_kernel<<<dim3((n + EMD_THREADS - 1) / EMD_THREADS, slices, B), EMD_THREADS, 0, s>>>(
+      xyz1_dev, xyz2_dev, match_dev, n, m, slices, partial);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  const long tot = (long)B * n * 3;
+  emd_grad1_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(partial, B, n, slices, grad1_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}

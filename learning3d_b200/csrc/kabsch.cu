@@ -1,0 +1,208 @@
+// Batched 3x3 Kabsch / SVD-head tail (sm_100a).
+//
+// Replaces the tail of SVDHead.forward (utils/svd.py:29-58): centring, H = src_c * corr_c^T,
+// the Python `for i in range(B)` loop of torch.svd + torch.det + a host-synchronising
+// `if r_det < 0` branch (:38-51), and t = -R*mean(src) + mean(src_corr) (:58).
+// One CTA per batch item reduces the means and H over N (fp64 accumulation), thread 0 then runs a
+// one-sided Jacobi SVD of the 3x3 in fp64 (a handful of rotations), fixes the determinant by
+// negating the right singular vector of the SMALLEST singular value (v * diag(1,1,-1), :44-45)
+// and writes R, t.  No host round trip, one launch for the whole batch.  Latency bound by design
+// (36 B in / 48 B out per item once H is known).
+#include "common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+namespace l3d {
+
+__device__ void kabsch_from_H(const double Hin[9], const float mu_s[3], const float mu_c[3],
+                              float* __restrict__ R_out, float* __restrict__ t_out) {
+  double A[3][3], V[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { A[i][j] = Hin[i * 3 + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+
+  // one-sided (Hestenes) Jacobi: rotate column pairs of A (and V) until mutually orthogonal
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int pair = 0; pair < 3; ++pair) {
+      const int p = (pair == 2) ? 1 : 0;
+      const int q = (pair == 0) ? 1 : 2;
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        alpha += A[i][p] * A[i][p];
+        beta += A[i][q] * A[i][q];
+        gamma += A[i][p] * A[i][q];
+      }
+      if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - s * aq;
+          A[i][q] = s * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+        rotated = true;
+      }
+    }
+    if (!rotated) break;
+  }
+  // singular values = column norms; sort descending (torch.svd order) by swapping columns
+  double sig[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const int a = (pass == 1) ? 1 : 0, b = (pass == 1) ? 2 : 1;   // (0,1), (1,2), (0,1)
+    if (sig[a] < sig[b]) {
+      const double ts = sig[a]; sig[a] = sig[b]; sig[b] = ts;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double tv = A[i][a]; A[i][a] = A[i][b]; A[i][b] = tv;
+        tv = V[i][a]; V[i][a] = V[i][b]; V[i][b] = tv;
+      }
+    }
+  }
+  // U = A * Sigma^-1; a vanishing singular value leaves its direction free: complete the basis
+  double U[3][3];
+  const double tiny = 1e-300;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double inv = sig[j] > tiny ? 1.0 / sig[j] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i][j] = A[i][j] * inv;
+  }
+  if (sig[2] > 1e-14 * sig[0] && sig[2] > tiny) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i][2] = A[i][2] / sig[2];
+  } else {
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+  }
+  // r = v u^T; if det(r) < 0: v <- v * diag(1,1,-1)   (svd.py:40-45)
+  double R[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[i][j] = V[i][0] * U[j][0] + V[i][1] * U[j][1] + V[i][2] * U[j][2];
+  const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) -
+                     R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                     R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+  if (det < 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[i][j] -= 2.0 * V[i][2] * U[j][2];
+  }
+  float Rf[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { Rf[i * 3 + j] = (float)R[i][j]; R_out[i * 3 + j] = Rf[i * 3 + j]; }
+  // t = matmul(-R, mean(src)) + mean(src_corr)   (svd.py:58), fp32 like the reference
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float acc = fmaf(-Rf[i * 3 + 2], mu_s[2], fmaf(-Rf[i * 3 + 1], mu_s[1], (-Rf[i * 3]) * mu_s[0]));
+    t_out[i] = acc + mu_c[i];
+  }
+}
+
+__global__ void __launch_bounds__(32) kabsch_kernel(const float* __restrict__ H, const float* __restrict__ mu_s,
+                                                    const float* __restrict__ mu_c, int B,
+                                                    float* __restrict__ R, float* __restrict__ t) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double h[9];
+  float ms[3], mc[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h[i] = (double)H[(size_t)b * 9 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { ms[i] = mu_s[b * 3 + i]; mc[i] = mu_c[b * 3 + i]; }
+  kabsch_from_H(h, ms, mc, R + (size_t)b * 9, t + (size_t)b * 3);
+}
+
+// src, corr: [B,3,N].  One CTA per batch item.
+constexpr int SVDH_THREADS = 256;
+__global__ void __launch_bounds__(SVDH_THREADS) svd_head_tail_kernel(const float* __restrict__ src,
+                                                                     const float* __restrict__ corr, int N,
+                                                                     float* __restrict__ R,
+                                                                     float* __restrict__ t) {
+  __shared__ double red[SVDH_THREADS / 32][15];
+  __shared__ double tot[15];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* s = src + (size_t)b * 3 * N;
+  const float* c = corr + (size_t)b * 3 * N;
+  // sums: 0-2 sum src, 3-5 sum corr, 6-14 sum src_i*corr_j ; H = sum s c^T - N mu_s mu_c^T
+  double acc[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) acc[i] = 0.0;
+  for (int n = tid; n < N; n += SVDH_THREADS) {
+    const double sv[3] = {(double)s[n], (double)s[N + n], (double)s[2 * N + n]};
+    const double cv[3] = {(double)c[n], (double)c[N + n], (double)c[2 * N + n]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { acc[i] += sv[i]; acc[3 + i] += cv[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[6 + i * 3 + j] += sv[i] * cv[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(L3D_FULL_MASK, acc[i], o);
+    if (lane == 0) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < 15) {
+    double v = 0.0;
+    for (int w = 0; w < SVDH_THREADS / 32; ++w) v += red[w][tid];
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double inv = 1.0 / (double)N;
+    double h[9];
+    float ms[3], mc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ms[i] = (float)(tot[i] * inv); mc[i] = (float)(tot[3 + i] * inv); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) h[i * 3 + j] = tot[6 + i * 3 + j] - tot[i] * tot[3 + j] * inv;
+    kabsch_from_H(h, ms, mc, R + (size_t)b * 9, t + (size_t)b * 3);
+  }
+}
+
+}  // namespace l3d
+
+using namespace l3d;
+
+extern "C" int l3d_kabsch3x3_batched(const float* H_dev, const float* src_mean_dev,
+                                     const float* corr_mean_dev, int B, float* R_dev, float* t_dev,
+                                     void* stream) {
+  if (!H_dev || !src_mean_dev || !corr_mean_dev || !R_dev || !t_dev || B < 0) return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  kabsch_kernel<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(H_dev, src_mean_dev, corr_mean_dev, B,
+                                                                R_dev, t_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+extern "C" int l3d_svd_head_tail(const float* src_dev, const float* src_corr_dev, int B, int N,
+                                 float* R_dev, float* t_dev, void* stream) {
+  if (!src_dev || !src_corr_dev || !R_dev || !t_dev || B < 0 || N < 1) return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  svd_head_tail_kernel<<<B, SVDH_THREADS, 0, (cudaStream_t)stream>>>(src_dev, src_corr_dev, N, R_dev, t_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}

@@ -4,6 +4,7 @@ As in the reference, the names re-exported here are the model_common_utils varia
 import at utils/__init__.py:5-14 shadows the ppfnet_util ones); the pointconv_util / ppfnet_util
 variants stay reachable under their own module paths.
 """
+from .svd import SVDHead
 from .ppfnet_util import angle_difference, sample_and_group, sample_and_group_multi
 from .model_common_utils import (
     knn,

@@ -1,0 +1,54 @@
+"""Drop-in for learning3d/utils/svd.py:5-59 (DCP's SVD head).
+
+Same constructor, state_dict key (`reflect`) and forward contract.  The soft-correspondence front
+half (score GEMM, softmax, src_corr GEMM: dense contractions) stays on torch /
+cuBLAS; the tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
+branch (svd.py:38-51) and t — is ONE launch of l3d_svd_head_tail for the whole batch.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _C
+
+
+class _SVDTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, src_corr):
+        B, _, N = src.shape
+        R = torch.empty((B, 3, 3), dtype=torch.float32, device=src.device)
+        t = torch.empty((B, 3), dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(src), _C.ptr(src_corr), B, N, _C.ptr(R),
+                                                _C.ptr(t), _C.stream()), "SVDHead")
+        ctx.mark_non_differentiable(R, t)
+        return R, t
+
+
+class SVDHead(nn.Module):
+    def __init__(self, emb_dims, input_shape="bnc"):
+        super(SVDHead, self).__init__()
+        self.emb_dims = emb_dims
+        self.reflect = nn.Parameter(torch.eye(3), requires_grad=False)
+        self.reflect[2, 2] = -1
+        self.input_shape = input_shape
+
+    def forward(self, *input):
+        src_embedding, tgt_embedding, src, tgt = input[0], input[1], input[2], input[3]
+        if self.input_shape == "bnc":
+            src = src.permute(0, 2, 1)
+            tgt = tgt.permute(0, 2, 1)
+        d_k = src_embedding.size(1)
+        scores = torch.matmul(src_embedding.transpose(2, 1).contiguous(), tgt_embedding) / math.sqrt(d_k)
+        scores = torch.softmax(scores, dim=2)
+        src_corr = torch.matmul(tgt, scores.transpose(2, 1).contiguous())
+        if torch.is_grad_enabled() and (src_corr.requires_grad or src.requires_grad):
+            raise NotImplementedError(
+                "learning3d_b200.SVDHead: the differentiable (training) path through the 3x3 SVD is not "
+                "built yet (SURVEY.md §8f); run under torch.no_grad() / eval as examples/test_dcp.py does")
+        src = _C.require_cuda(src, "src")
+        src_corr = _C.require_cuda(src_corr, "src_corr")
+        # NOTE: as in the reference's eval use (examples/test_dcp.py) R, t carry no gradient here; the
+        # differentiable SVD backward is part of the "next" rows (training path).
+        return _SVDTail.apply(src, src_corr)

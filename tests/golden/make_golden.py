@@ -126,15 +126,41 @@ def gen_group():
     save("group", **{k: v.numpy() for k, v in out.items()})
 
 
+def gen_svd():
+    """SVDHead (utils/svd.py:5-59) on CPU with matched embeddings (peaky soft correspondences, so H is
+    well conditioned): a rigid-motion case and a mirrored case that takes the det < 0 branch."""
+    from learning3d.utils.svd import SVDHead
+    torch.manual_seed(5)
+    B, d, N = 4, 64, 128
+    head = SVDHead(d)
+    src = torch.rand(B, N, 3) - 0.5
+    ang = torch.rand(B) * 1.2
+    c, s_ = torch.cos(ang), torch.sin(ang)
+    Rz = torch.zeros(B, 3, 3); Rz[:, 0, 0] = c; Rz[:, 0, 1] = -s_; Rz[:, 1, 0] = s_; Rz[:, 1, 1] = c; Rz[:, 2, 2] = 1
+    tgt = torch.matmul(src, Rz.transpose(1, 2)) + torch.rand(B, 1, 3)
+    tgt[2:, :, 0] *= -1                               # items 2,3: mirrored target -> det(v u^T) < 0
+    emb = torch.randn(B, d, N) * 3.0
+    perm = torch.stack([torch.randperm(N) for _ in range(B)])
+    tgt = torch.gather(tgt, 1, perm[..., None].expand(B, N, 3))          # shuffle the target order
+    tgt_emb = torch.gather(emb, 2, perm[:, None, :].expand(B, d, N)) + 0.05 * torch.randn(B, d, N)
+    R, t = head(emb, tgt_emb, src, tgt)
+    scores = torch.softmax(torch.matmul(emb.transpose(2, 1).contiguous(), tgt_emb) / d ** 0.5, dim=2)
+    src_corr = torch.matmul(tgt.permute(0, 2, 1), scores.transpose(2, 1).contiguous())
+    save("svd_head", src_emb=emb.numpy(), tgt_emb=tgt_emb.numpy(), src=src.numpy(), tgt=tgt.numpy(),
+         src_corr=src_corr.numpy(), R=R.numpy(), t=t.numpy())
+
+
 if __name__ == "__main__":
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     os.environ.setdefault("TORCH_EXTENSIONS_DIR", tempfile.mkdtemp(prefix="l3dref_ext_"))
     os.environ["CC"] = "/usr/bin/gcc"; os.environ["CXX"] = "/usr/bin/g++"
     import_reference()
-    which = sys.argv[1:] or ["knn", "chamfer", "group"]
+    which = sys.argv[1:] or ["knn", "chamfer", "group", "svd"]
     if "knn" in which:
         gen_knn()
     if "chamfer" in which:
         gen_chamfer()
     if "group" in which:
         gen_group()
+    if "svd" in which:
+        gen_svd()

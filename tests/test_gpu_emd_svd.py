@@ -1,0 +1,109 @@
+"""GPU parity: EMD (approxmatch/matchcost/grads) and the SVD-head tail against the oracle; tolerance 1e-5
+relative on cost / R / t as BASELINE.json's north_star states (match entries: absolute 1e-5 of unit mass)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import emd as oe
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _emd(a_np, b_np):
+    from learning3d_b200.losses.cuda.emd_torch.pkg.layer import EMDFunction
+    a = T(a_np).requires_grad_(True)
+    b = T(b_np).requires_grad_(True)
+    cost = EMDFunction.apply(a, b)
+    return a, b, cost
+
+
+@pytest.mark.parametrize("B,n,m", [(8, 1024, 1024), (2, 256, 256), (3, 100, 333), (1, 512, 128), (1, 1500, 1500)])
+def test_emd_forward_backward_vs_oracle(B, n, m):
+    rng = np.random.default_rng(n + m)
+    a_np = rng.random((B, n, 3), dtype=np.float32)
+    b_np = rng.random((B, m, 3), dtype=np.float32)
+    a, b, cost = _emd(a_np, b_np)
+    ocost, omatch = oe.emd_forward(a_np, b_np)
+    np.testing.assert_allclose(cost.detach().cpu().numpy(), ocost, rtol=1e-5)
+    # the saved matching itself
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    match = torch.empty((B, n, m), device=DEV)
+    c2 = torch.empty((B,), device=DEV)
+    ws = torch.empty(int(lib.l3d_emd_forward_ws_bytes(B, n, m)), dtype=torch.uint8, device=DEV)
+    _C.check(lib.l3d_emd_forward(_C.ptr(a.detach()), _C.ptr(b.detach()), B, n, m, _C.ptr(c2), _C.ptr(match),
+                                 _C.ptr(ws), _C.stream()))
+    np.testing.assert_allclose(match.cpu().numpy(), omatch, atol=1e-5, rtol=1e-4)
+    assert torch.equal(c2, cost.detach())                       # deterministic
+    # gradients (matching held constant; grad_output ignored exactly like the reference)
+    (cost * 7.0).sum().backward()
+    og1, og2 = oe.grads(a_np, b_np, omatch)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), og1, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), og2, rtol=1e-4, atol=1e-5)
+
+
+def test_emd_loss_module_intended_semantics():
+    from learning3d_b200.losses import EMDLoss
+    rng = np.random.default_rng(3)
+    a_np = rng.random((8, 1024, 3), dtype=np.float32)        # BASELINE config C5 shape
+    b_np = rng.random((8, 1024, 3), dtype=np.float32)
+    a = T(a_np).requires_grad_(True)
+    loss = EMDLoss()(a, T(b_np))
+    ocost, omatch = oe.emd_forward(a_np, b_np)
+    want = ocost.mean() / 1024
+    assert abs(loss.item() - want) <= 1e-5 * abs(want)
+    loss.backward()
+    og1, _ = oe.grads(a_np, b_np, omatch)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), og1 / (8 * 1024), rtol=1e-4, atol=1e-9)
+
+
+def test_emd_input_checks():
+    from learning3d_b200.losses.cuda.emd_torch.pkg.layer import EMDLoss
+    with pytest.raises(RuntimeError):
+        EMDLoss()(torch.rand(1, 8, 3), torch.rand(1, 8, 3))            # CPU tensors (CHECK_CUDA)
+    x = torch.rand(1, 3, 8, device=DEV).transpose(1, 2)
+    with pytest.raises(RuntimeError):
+        EMDLoss()(x, x)                                                # non-contiguous (CHECK_CONTIGUOUS)
+
+
+def test_svd_head_golden(golden_dir):
+    from learning3d_b200.utils import SVDHead
+    g = np.load(f"{golden_dir}/svd_head.npz")
+    head = SVDHead(64).to(DEV)
+    assert "reflect" in head.state_dict()
+    with torch.no_grad():
+        R, t = head(T(g["src_emb"]), T(g["tgt_emb"]), T(g["src"]), T(g["tgt"]))
+    np.testing.assert_allclose(R.cpu().numpy(), g["R"], atol=1e-5)     # includes two det<0 items
+    np.testing.assert_allclose(t.cpu().numpy(), g["t"], atol=1e-5)
+
+
+def test_svd_tail_vs_oracle_and_kabsch_entry():
+    from learning3d_b200 import _C
+    rng = np.random.default_rng(8)
+    B, N = 32, 1024                                           # BASELINE config C3 shape
+    src = rng.standard_normal((B, 3, N)).astype(np.float32)
+    A = rng.standard_normal((B, 3, 3)).astype(np.float32)     # general linear maps: both det signs
+    corr = (A @ src + rng.standard_normal((B, 3, 1)).astype(np.float32) +
+            0.01 * rng.standard_normal((B, 3, N)).astype(np.float32)).astype(np.float32)
+    R = torch.empty((B, 3, 3), device=DEV); t = torch.empty((B, 3), device=DEV)
+    _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(T(src)), _C.ptr(T(corr)), B, N, _C.ptr(R), _C.ptr(t), _C.stream()))
+    torch.cuda.synchronize()
+    oR, ot = oe.svd_head_tail(src, corr)
+    np.testing.assert_allclose(R.cpu().numpy(), oR, atol=1e-5)
+    np.testing.assert_allclose(t.cpu().numpy(), ot, atol=2e-5)
+    Rn = R.cpu().numpy()
+    np.testing.assert_allclose(Rn @ Rn.transpose(0, 2, 1), np.tile(np.eye(3), (B, 1, 1)), atol=1e-6)
+    assert np.allclose(np.linalg.det(Rn), 1.0, atol=1e-5)
+    # the H-level entry point gives the same rotation
+    mu_s = src.mean(2); mu_c = corr.mean(2)
+    H = ((src - mu_s[..., None]) @ (corr - mu_c[..., None]).transpose(0, 2, 1)).astype(np.float32)
+    R2 = torch.empty((B, 3, 3), device=DEV); t2 = torch.empty((B, 3), device=DEV)
+    Hd, ms, mc = T(H), T(mu_s), T(mu_c)
+    _C.check(_C.lib().l3d_kabsch3x3_batched(_C.ptr(Hd), _C.ptr(ms), _C.ptr(mc), B, _C.ptr(R2), _C.ptr(t2), _C.stream()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(R2.cpu().numpy(), oR, atol=1e-5)

@@ -212,7 +212,8 @@ def test_reference_cuda_kernels_agree_with_oracle(ref, oracle_mod):
     for cloud in (xyz, np.tile(xyz[:, :256], (1, 4, 1))):
         n = cloud.shape[1]
         temp = torch.full((B, n), 1e10, device=DEV); fi = torch.empty((B, 300), dtype=torch.int32, device=DEV)
-        ref.ref_fps(B, n, 300, _p(T(cloud)), _p(temp), _p(fi), s)
+        cd_ = T(cloud)
+        ref.ref_fps(B, n, 300, _p(cd_), _p(temp), _p(fi), s)
         torch.cuda.synchronize()
         want, wtemp = og.pn2_fps(cloud, 300)
         assert np.array_equal(fi.cpu().numpy(), want)
@@ -221,10 +222,12 @@ def test_reference_cuda_kernels_agree_with_oracle(ref, oracle_mod):
     feats = rng.standard_normal((B, 10, N)).astype(np.float32)
     gi = rng.integers(0, N, (B, 64, 8)).astype(np.int32)
     out = torch.empty((B, 10, 64, 8), device=DEV)
-    ref.ref_group_points(B, 10, N, 64, 8, _p(T(feats)), _p(T(gi)), _p(out), s)
+    fd, gid = T(feats), T(gi)          # keep the device tensors alive across the async launches
+    ref.ref_group_points(B, 10, N, 64, 8, _p(fd), _p(gid), _p(out), s)
     w = rng.random((B, S, 3)).astype(np.float32); ti = rng.integers(0, N, (B, S, 3)).astype(np.int32)
     o3 = torch.empty((B, 10, S), device=DEV)
-    ref.ref_three_interpolate(B, 10, N, S, _p(T(feats)), _p(T(ti)), _p(T(w)), _p(o3), s)
+    tid, wd = T(ti), T(w)
+    ref.ref_three_interpolate(B, 10, N, S, _p(fd), _p(tid), _p(wd), _p(o3), s)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), og.pn2_group_points(feats, gi))
     assert np.array_equal(o3.cpu().numpy(), og.pn2_three_interpolate(feats, ti, w))
