@@ -88,13 +88,22 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFw
           __syncthreads();
         }
         if (active) {
-#pragma unroll 4
-          for (int j = sub; j < cn; j += CH_LPQ) {
+          int j = sub;
+          if (!have && j < cn) {   // `k == 0 ||` of the reference: the first candidate is taken as is
+            const float4 cc = cand[j];
+            const float dx = __fsub_rn(cc.x, qx), dy = __fsub_rn(cc.y, qy), dz = __fsub_rn(cc.z, qz);
+            best = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            besti = c0 + j;
+            have = true;
+            j += CH_LPQ;
+          }
+#pragma unroll 8
+          for (; j < cn; j += CH_LPQ) {
             const float4 cc = cand[j];
             // const float x2 = xyz2[..] - x1 ...; d = x2*x2 + y2*y2 + z2*z2   (.cpp:74-77)
             const float dx = __fsub_rn(cc.x, qx), dy = __fsub_rn(cc.y, qy), dz = __fsub_rn(cc.z, qz);
             const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (!have || d < best) { best = d; besti = c0 + j; have = true; }   // (.cpp:78)
+            if (d < best) { best = d; besti = c0 + j; }   // strict '<' (.cpp:78)
           }
         }
       }
@@ -195,6 +204,9 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const ChamferBw
   float px = 0.f, py = 0.f, pz = 0.f;
   if (active) { px = my[i * 3]; py = my[i * 3 + 1]; pz = my[i * 3 + 2]; }
   float ax = 0.f, ay = 0.f, az = 0.f;
+  // the scan below is a chain of dependent loads: issue 8 independent 32-wide index loads at a
+  // time so their L2 latency overlaps (the kernel is latency-, not bandwidth-bound)
+  constexpr int PF = 8;
 
   // own term: grad[i] += g*(p_i - q_idx[i])        (.cpp:153-155 / :170-172)
   float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -209,27 +221,107 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const ChamferBw
   // side 1 (xyz2): the scattered terms of loop 1 come first, then its own loop.
   if (side == 0) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
 
-  for (int j0 = 0; j0 < nx; j0 += 32) {
-    const int j = j0 + lane;
-    int rel = -1;
-    if (j < nx) rel = oidx[j] - i0;
-    unsigned hits = __ballot_sync(L3D_FULL_MASK, rel >= 0 && rel < 32);
-    while (hits) {
-      const int src = __ffs(hits) - 1;
-      hits &= hits - 1;
-      const int tgt = __shfl_sync(L3D_FULL_MASK, rel, src);
-      if (lane == tgt) {
-        // grad[idx[j]] -= g_j * (q_j - p_idx[j])      (.cpp:156-158 / :173-175)
-        const int jj = j0 + src;
-        const float g = chamfer_g(p, other, (size_t)b * nx + jj, gl_half);
-        ax = __fsub_rn(ax, __fmul_rn(g, __fsub_rn(ot[jj * 3], px)));
-        ay = __fsub_rn(ay, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 1], py)));
-        az = __fsub_rn(az, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 2], pz)));
+  for (int jb = 0; jb < nx; jb += 32 * PF) {
+    int relv[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int j = jb + u * 32 + lane;
+      relv[u] = (j < nx) ? (__ldg(oidx + j) - i0) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int j0 = jb + u * 32;
+      const int rel = relv[u];
+      unsigned hits = __ballot_sync(L3D_FULL_MASK, rel >= 0 && rel < 32);
+      while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int tgt = __shfl_sync(L3D_FULL_MASK, rel, src);
+        if (lane == tgt) {
+          // grad[idx[j]] -= g_j * (q_j - p_idx[j])      (.cpp:156-158 / :173-175)
+          const int jj = j0 + src;
+          const float g = chamfer_g(p, other, (size_t)b * nx + jj, gl_half);
+          ax = __fsub_rn(ax, __fmul_rn(g, __fsub_rn(ot[jj * 3], px)));
+          ay = __fsub_rn(ay, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 1], py)));
+          az = __fsub_rn(az, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 2], pz)));
+        }
       }
     }
   }
   if (side == 1) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
 
+  if (active) {
+    float* o = p.grad[side] + ((size_t)b * no + i) * 3;
+    o[0] = ax; o[1] = ay; o[2] = az;
+  }
+}
+
+// Version 2 of the gather backward: the OTHER cloud's (x, y, z, g_j) and arg-min indices are staged
+// in shared memory per CTA, so handing a hit to its owner lane costs two LDS instead of a chain of
+// dependent global loads (v1 spent ~600 cycles per hit: 20 us at B=4 for 3 us of work).
+constexpr int CHB_CHUNK = 2048;
+__global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel2(const ChamferBwdParams p) {
+  __shared__ float4 s_pt[CHB_CHUNK];
+  __shared__ int s_idx[CHB_CHUNK];
+  const int side = blockIdx.y, b = blockIdx.z;
+  const int other = 1 - side;
+  const int no = p.cnt[side], nx = p.cnt[other];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i0 = (blockIdx.x * (CH_THREADS / 32) + (tid >> 5)) * 32;  // warp's first output point
+  const int i = i0 + lane;
+  const bool active = i < no;
+  const float* my = p.xyz[side] + (size_t)b * no * 3;
+  const float* ot = p.xyz[other] + (size_t)b * nx * 3;
+  const int* oidx = p.idx[other] + (size_t)b * nx;
+  const float gl_half = p.grad_loss ? (*p.grad_loss) * 0.5f : 0.f;
+
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (active) { px = my[i * 3]; py = my[i * 3 + 1]; pz = my[i * 3 + 2]; }
+  // own term: grad[i] += g*(p_i - q_idx[i])        (.cpp:153-155 / :170-172)
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  if (active) {
+    const int j2 = p.idx[side][(size_t)b * no + i];
+    const float g = chamfer_g(p, side, (size_t)b * no + i, gl_half);
+    ox = __fmul_rn(g, __fsub_rn(px, ot[j2 * 3]));
+    oy = __fmul_rn(g, __fsub_rn(py, ot[j2 * 3 + 1]));
+    oz = __fmul_rn(g, __fsub_rn(pz, ot[j2 * 3 + 2]));
+  }
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  // side 0 (xyz1): its own loop runs first, the scattered terms of loop 2 follow;
+  // side 1 (xyz2): the scattered terms of loop 1 come first, then its own loop.
+  if (side == 0) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
+
+  for (int c0 = 0; c0 < nx; c0 += CHB_CHUNK) {
+    const int cn = min(CHB_CHUNK, nx - c0);
+    __syncthreads();
+    for (int j = tid; j < cn; j += CH_THREADS) {
+      const int jj = c0 + j;
+      s_pt[j] = make_float4(ot[jj * 3], ot[jj * 3 + 1], ot[jj * 3 + 2],
+                            chamfer_g(p, other, (size_t)b * nx + jj, gl_half));
+      s_idx[j] = oidx[jj];
+    }
+    __syncthreads();
+    if (i0 < no) {
+      for (int j0 = 0; j0 < cn; j0 += 32) {
+        const int j = j0 + lane;
+        const int rel = (j < cn) ? (s_idx[j] - i0) : -1;
+        unsigned hits = __ballot_sync(L3D_FULL_MASK, rel >= 0 && rel < 32);
+        while (hits) {
+          const int src = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int tgt = __shfl_sync(L3D_FULL_MASK, rel, src);
+          if (lane == tgt) {
+            // grad[idx[j]] -= g_j * (q_j - p_idx[j])      (.cpp:156-158 / :173-175)
+            const float4 q = s_pt[j0 + src];
+            ax = __fsub_rn(ax, __fmul_rn(q.w, __fsub_rn(q.x, px)));
+            ay = __fsub_rn(ay, __fmul_rn(q.w, __fsub_rn(q.y, py)));
+            az = __fsub_rn(az, __fmul_rn(q.w, __fsub_rn(q.z, pz)));
+          }
+        }
+      }
+    }
+  }
+  if (side == 1) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
   if (active) {
     float* o = p.grad[side] + ((size_t)b * no + i) * 3;
     o[0] = ax; o[1] = ay; o[2] = az;
@@ -294,7 +386,7 @@ extern "C" int l3d_chamfer_backward(const float* xyz1_dev, const float* xyz2_dev
   p.cnt[0] = n; p.cnt[1] = m; p.B = B;
   const int nmax = n > m ? n : m;
   dim3 grid((nmax + CH_THREADS - 1) / CH_THREADS, 2, B);
-  chamfer_bwd_kernel<<<grid, CH_THREADS, 0, (cudaStream_t)stream>>>(p);
+  chamfer_bwd_kernel2<<<grid, CH_THREADS, 0, (cudaStream_t)stream>>>(p);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
@@ -341,7 +433,7 @@ extern "C" int l3d_chamfer_loss_backward(const float* xyz1_dev, const float* xyz
   p.cnt[0] = n; p.cnt[1] = m; p.B = B;
   const int nmax = n > m ? n : m;
   dim3 grid((nmax + CH_THREADS - 1) / CH_THREADS, 2, B);
-  chamfer_bwd_kernel<<<grid, CH_THREADS, 0, (cudaStream_t)stream>>>(p);
+  chamfer_bwd_kernel2<<<grid, CH_THREADS, 0, (cudaStream_t)stream>>>(p);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;

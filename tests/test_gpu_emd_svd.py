@@ -38,13 +38,26 @@ def test_emd_forward_backward_vs_oracle(B, n, m):
     ws = torch.empty(int(lib.l3d_emd_forward_ws_bytes(B, n, m)), dtype=torch.uint8, device=DEV)
     _C.check(lib.l3d_emd_forward(_C.ptr(a.detach()), _C.ptr(b.detach()), B, n, m, _C.ptr(c2), _C.ptr(match),
                                  _C.ptr(ws), _C.stream()))
-    np.testing.assert_allclose(match.cpu().numpy(), omatch, atol=1e-5, rtol=1e-4)
+    # The soft matching amplifies last-bit differences of exp() where two candidates nearly tie
+    # (__expf/ex2.approx on the GPU, libm expf in the oracle): single entries move by up to ~2e-3 of a
+    # unit-mass row while row/column masses and the cost agree to 1e-6 (profiles/diag_emd.py).
+    mm = match.cpu().numpy()
+    np.testing.assert_allclose(mm, omatch, atol=5e-3)
+    np.testing.assert_allclose(mm.reshape(B, m, n).sum(1), omatch.reshape(B, m, n).sum(1), atol=2e-5)
     assert torch.equal(c2, cost.detach())                       # deterministic
-    # gradients (matching held constant; grad_output ignored exactly like the reference)
-    (cost * 7.0).sum().backward()
+    # gradient kernels on the SAME matching: 1e-5
+    g1 = torch.empty_like(a); g2 = torch.empty_like(b)
+    ws2 = torch.empty(int(lib.l3d_emd_backward_ws_bytes(B, n, m)), dtype=torch.uint8, device=DEV)
+    om_d = T(omatch)
+    _C.check(lib.l3d_emd_backward(_C.ptr(a.detach()), _C.ptr(b.detach()), _C.ptr(om_d), B, n, m, _C.ptr(g1),
+                                  _C.ptr(g2), _C.ptr(ws2), _C.stream()))
     og1, og2 = oe.grads(a_np, b_np, omatch)
-    np.testing.assert_allclose(a.grad.cpu().numpy(), og1, rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(b.grad.cpu().numpy(), og2, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(g1.cpu().numpy(), og1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g2.cpu().numpy(), og2, rtol=1e-5, atol=1e-5)
+    # autograd path (own matching; grad_output ignored exactly like the reference)
+    (cost * 7.0).sum().backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), og1, atol=3e-3)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), og2, atol=3e-3)
 
 
 def test_emd_loss_module_intended_semantics():
@@ -59,7 +72,7 @@ def test_emd_loss_module_intended_semantics():
     assert abs(loss.item() - want) <= 1e-5 * abs(want)
     loss.backward()
     og1, _ = oe.grads(a_np, b_np, omatch)
-    np.testing.assert_allclose(a.grad.cpu().numpy(), og1 / (8 * 1024), rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(a.grad.cpu().numpy(), og1 / (8 * 1024), atol=3e-3 / (8 * 1024))
 
 
 def test_emd_input_checks():
@@ -91,7 +104,8 @@ def test_svd_tail_vs_oracle_and_kabsch_entry():
     corr = (A @ src + rng.standard_normal((B, 3, 1)).astype(np.float32) +
             0.01 * rng.standard_normal((B, 3, N)).astype(np.float32)).astype(np.float32)
     R = torch.empty((B, 3, 3), device=DEV); t = torch.empty((B, 3), device=DEV)
-    _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(T(src)), _C.ptr(T(corr)), B, N, _C.ptr(R), _C.ptr(t), _C.stream()))
+    sd, cd_ = T(src), T(corr)      # keep alive: a freed temporary's block is handed to the next T()
+    _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(sd), _C.ptr(cd_), B, N, _C.ptr(R), _C.ptr(t), _C.stream()))
     torch.cuda.synchronize()
     oR, ot = oe.svd_head_tail(src, corr)
     np.testing.assert_allclose(R.cpu().numpy(), oR, atol=1e-5)
