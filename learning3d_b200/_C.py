@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libl3d_b200.so")
+# L3D_B200_LIB lets profiles/tune_knn.py load experimental builds of the same library
+LIB_PATH = os.environ.get("L3D_B200_LIB") or os.path.join(_HERE, "libl3d_b200.so")
 _lib = None
 
 _P = ctypes.c_void_p

@@ -15,6 +15,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 struct HostCtx {
   std::mutex mu;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;
   void* in = nullptr;  size_t in_cap = 0;
   void* out = nullptr; size_t out_cap = 0;
   int ensure(size_t in_bytes, size_t out_bytes) {
@@ -60,13 +61,38 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   const size_t out_bytes = (size_t)B * N * k * sizeof(int64_t);
   int rc = l3d::g_host.ensure(in_bytes, out_bytes);
   if (rc) return rc;
-  cudaStream_t s = l3d::g_host.stream;
-  cudaError_t e = cudaMemcpyAsync(l3d::g_host.in, x_host, in_bytes, cudaMemcpyHostToDevice, s);
+  // The call is PCIe-bound: 8*k bytes of int64 indices return per 12 bytes of input.  The batch is
+  // cut into slices that ping-pong over two streams so the device-to-host copy of slice i overlaps
+  // the kernel of slice i+1 (clouds are independent; each slice is a whole number of clouds).
+  cudaError_t e;
+  if (!l3d::g_host.stream2) {
+    e = cudaStreamCreateWithFlags(&l3d::g_host.stream2, cudaStreamNonBlocking);
+    if (e) return (int)e;
+  }
+  cudaStream_t st[2] = {l3d::g_host.stream, l3d::g_host.stream2};
+  const int nslice = B >= 8 ? 4 : (B >= 2 ? 2 : 1);
+  const float* din = (const float*)l3d::g_host.in;
+  int64_t* dout = (int64_t*)l3d::g_host.out;
+  int b0 = 0;
+  for (int i = 0; i < nslice; ++i) {
+    const int b1 = (int)((long)B * (i + 1) / nslice);
+    const int nb = b1 - b0;
+    if (nb > 0) {
+      cudaStream_t s = st[i & 1];
+      const size_t io = (size_t)b0 * 3 * N, oo = (size_t)b0 * N * k;
+      e = cudaMemcpyAsync((void*)(din + io), x_host + io, (size_t)nb * 3 * N * sizeof(float),
+                          cudaMemcpyHostToDevice, s);
+      if (e) return (int)e;
+      rc = l3d_knn_expansion(din + io, nb, N, k, dout + oo, nullptr, s);
+      if (rc) return rc;
+      e = cudaMemcpyAsync(idx_host + oo, dout + oo, (size_t)nb * N * k * sizeof(int64_t),
+                          cudaMemcpyDeviceToHost, s);
+      if (e) return (int)e;
+    }
+    b0 = b1;
+  }
+  e = cudaStreamSynchronize(st[0]);
   if (e) return (int)e;
-  rc = l3d_knn_expansion((const float*)l3d::g_host.in, B, N, k, (int64_t*)l3d::g_host.out, nullptr, s);
-  if (rc) return rc;
-  e = cudaMemcpyAsync(idx_host, l3d::g_host.out, out_bytes, cudaMemcpyDeviceToHost, s);
-  if (e) return (int)e;
-  e = cudaStreamSynchronize(s);
+  e = cudaStreamSynchronize(st[1]);
   return (int)e;
 }

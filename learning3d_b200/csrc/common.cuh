@@ -154,6 +154,99 @@ __device__ __forceinline__ void warp_bitonic_sort_keys(float (&v)[S], int lane) 
   }
 }
 
+// ---- second-generation selection network (v2) ----------------------------------------------
+// A (key, index) pair is packed into ONE 64-bit composite whose unsigned order is the selection
+// order: high word = order-preserving image of the fp32 key, low word = ~index (lower index ->
+// larger composite).  All-zero is the sentinel (worse than any real pair).  One comparison per
+// exchange instead of three, and a sorting network in which every exchange has the same
+// direction rule ("the lower lane keeps the larger composite"): the classic flip + half-cleaner
+// bitonic merger, so a stage is 2 SHFL + 2 ISETP + 1 PLOP3 + 2 SEL.
+__device__ __forceinline__ uint32_t f32_order(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unorder(uint32_t o) {
+  const uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long pack_pair(float key, uint32_t idx) {
+  // key + 0.0f folds -0.0 into +0.0 so that equal keys always produce equal high words
+  return ((unsigned long long)f32_order(key + 0.0f) << 32) | (unsigned long long)(~idx);
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  const uint32_t lo = __shfl_xor_sync(L3D_FULL_MASK, (uint32_t)v, m);
+  const uint32_t hi = __shfl_xor_sync(L3D_FULL_MASK, (uint32_t)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+// exchange with lane ^ m; the lane whose `bit` of the lane id is clear keeps the larger composite
+__device__ __forceinline__ unsigned long long cmpx_u64(unsigned long long c, int m, bool keep_big) {
+  const unsigned long long o = shfl_xor_u64(c, m);
+  return ((o > c) == keep_big) ? o : c;
+}
+// Sort 32 composites (one per lane) descending: lane 0 ends with the largest.
+__device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long long c, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    c = cmpx_u64(c, k2 - 1, (lane & (k2 >> 1)) == 0);          // flip
+#pragma unroll
+    for (int j = k2 >> 2; j > 0; j >>= 1) c = cmpx_u64(c, j, (lane & j) == 0);   // half-cleaners
+  }
+  return c;
+}
+// R independent 32-wide sorts interleaved stage by stage (ILP across rows).
+template <int R>
+__device__ __forceinline__ void warp_sort32_desc_x(unsigned long long (&c)[R], int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    const bool kb = (lane & (k2 >> 1)) == 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = cmpx_u64(c[r], k2 - 1, kb);
+#pragma unroll
+    for (int j = k2 >> 2; j > 0; j >>= 1) {
+      const bool kj = (lane & j) == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) c[r] = cmpx_u64(c[r], j, kj);
+    }
+  }
+}
+// Largest 32 of 64 composites (two per lane), sorted descending into one register per lane.
+__device__ __forceinline__ unsigned long long warp_top32_of64(unsigned long long a, unsigned long long b,
+                                                                int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    const bool kb = (lane & (k2 >> 1)) == 0;
+    a = cmpx_u64(a, k2 - 1, kb);
+    b = cmpx_u64(b, k2 - 1, kb);
+#pragma unroll
+    for (int j = k2 >> 2; j > 0; j >>= 1) {
+      const bool kj = (lane & j) == 0;
+      a = cmpx_u64(a, j, kj);
+      b = cmpx_u64(b, j, kj);
+    }
+  }
+  const unsigned long long br = shfl_xor_u64(b, 31);   // b reversed: pairs a[i] with b[31-i]
+  unsigned long long c = (br > a) ? br : a;             // bitonic sequence holding the best 32
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) c = cmpx_u64(c, j, (lane & j) == 0);
+  return c;
+}
+// Keys-only descending sort of 32 floats with the same uniform-direction network.
+__device__ __forceinline__ float warp_sort32_keys_desc(float v, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    {
+      const float o = __shfl_xor_sync(L3D_FULL_MASK, v, k2 - 1);
+      v = ((lane & (k2 >> 1)) == 0) ? fmaxf(v, o) : fminf(v, o);
+    }
+#pragma unroll
+    for (int j = k2 >> 2; j > 0; j >>= 1) {
+      const float o = __shfl_xor_sync(L3D_FULL_MASK, v, j);
+      v = ((lane & j) == 0) ? fmaxf(v, o) : fminf(v, o);
+    }
+  }
+  return v;
+}
+
 __device__ __forceinline__ int warp_inclusive_scan(int x, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {

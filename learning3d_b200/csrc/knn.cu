@@ -36,6 +36,17 @@ constexpr int KNN_THREADS = 256;
 constexpr int KNN_WARPS = KNN_THREADS / 32;
 constexpr int KNN_TILE = 1024;   // candidates per tile = 32 lanes x 32 registers
 constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
+#ifndef L3D_KNN_R
+#define L3D_KNN_R 2
+#endif
+// Register budget: left to ptxas' own heuristic by default (127 registers at R = 2, 2 CTAs/SM), which
+// measured fastest; forcing min-blocks 1..5 (48..167 registers) was 10-35 % slower (profiles/r01).
+#ifdef L3D_KNN_MIN_BLOCKS
+#define L3D_KNN_BOUNDS __launch_bounds__(KNN_THREADS, L3D_KNN_MIN_BLOCKS)
+#else
+#define L3D_KNN_BOUNDS __launch_bounds__(KNN_THREADS)
+#endif
+constexpr int KNN_R = L3D_KNN_R;  // query rows per warp on the k <= 24 path (tuned in profiles/r01)
 constexpr int KNN_SORT_MAX_N = 256;  // clouds this small may be sorted whole (8 keys per lane)
 
 struct KnnParams {
@@ -94,8 +105,9 @@ __device__ __forceinline__ float4 knn_padding() {
 }
 
 __device__ __forceinline__ float knn_val_xform(float key, int xform) {
-  if (xform == 1) return -key;
-  if (xform == 2) return sqrtf(-key);
+  // 0 - key (not -key): a zero distance comes out as +0.0 like the reference's
+  if (xform == 1) return 0.0f - key;
+  if (xform == 2) return sqrtf(0.0f - key);
   return key;
 }
 
@@ -272,18 +284,205 @@ __device__ __forceinline__ void knn_row(const KnnParams& p, const float4* __rest
   }
 }
 
+// ---- v2 row routine ---------------------------------------------------------------------------
+// Same algorithm as knn_row, re-engineered after the first ncu capture (profiles/r01): the
+// count / compaction pass kept 32 predicates alive in a bit-packed register (~400 LOP3/ISETP/VIADD
+// per row).  Here the survivors of a lane are a 32-bit mask built once (FSETP + predicated OR),
+// counted with POPC, and written by a short loop over the set bits that RE-EVALUATES the key
+// from shared memory (registers cannot be indexed dynamically; same inputs, same instructions ->
+// the same bits).  Survivors are stored as 64-bit composites and sorted with the uniform-direction
+// network of common.cuh.  KS = 1 keeps everything in one or two registers per lane.
+__device__ __forceinline__ void knn_store_packed(const KnnParams& p, long row, int pos,
+                                                 unsigned long long c) {
+  if (pos < p.k) {
+    const long o = row * p.k + pos;
+    const uint32_t ix = ~(uint32_t)c;
+    if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)ix;
+    else reinterpret_cast<int*>(p.out_idx)[o] = (int)ix;
+    if (p.out_val) p.out_val[o] = knn_val_xform(f32_unorder((uint32_t)(c >> 32)), p.val_xform);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void knn_row_v2(const KnnParams& p, const float4* __restrict__ packed,
+                                           unsigned long long* __restrict__ cbuf, const float4 q,
+                                           long row, int ntiles, int lane) {
+  constexpr int CAP = 64;
+  const int k = p.k;            // k <= 24 on this path
+  int base = 0;                 // composites carried over from earlier tiles (running top-k)
+  float kth = -INFINITY;
+  bool overflow = (p.force_slow != 0);
+  unsigned long long best = 0ull;   // lane l holds the l-th best composite after each tile
+
+  for (int t = 0; t < ntiles && !overflow; ++t) {
+    float d[32];
+    const float4* pt = packed + t * KNN_TILE + lane;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) d[e] = knn_key<MODE>(q, pt[e * 32]);
+
+    float m = d[0];
+#pragma unroll
+    for (int e = 1; e < 32; ++e) m = fmaxf(m, d[e]);
+    // k-th largest lane maximum: at least k keys of the tile are >= t0
+    const float t0 = __shfl_sync(L3D_FULL_MASK, warp_sort32_keys_desc(m, lane), k - 1);
+    const float thr = fmaxf(t0, kth);
+
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) mask |= (d[e] >= thr) ? (1u << e) : 0u;
+    const int cnt = __popc(mask);
+    const int incl = warp_inclusive_scan(cnt, lane);
+    const int total = __shfl_sync(L3D_FULL_MASK, incl, 31);
+    if (base + total > CAP) { overflow = true; break; }
+
+    if (base) {   // running top-k of the previous tiles goes first
+      if (lane < base) cbuf[lane] = best;
+    }
+    int off = base + incl - cnt;
+    while (mask) {
+      const int e = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int j = t * KNN_TILE + e * 32 + lane;
+      cbuf[off++] = pack_pair(knn_key<MODE>(q, packed[j]), (uint32_t)j);
+    }
+    __syncwarp();
+    const int n_in = base + total;
+    const unsigned long long a = (lane < n_in) ? cbuf[lane] : 0ull;
+    if (n_in <= 32) {
+      best = warp_sort32_desc(a, lane);
+    } else {
+      const unsigned long long b = (lane + 32 < n_in) ? cbuf[lane + 32] : 0ull;
+      best = warp_top32_of64(a, b, lane);
+    }
+    __syncwarp();
+    if (t + 1 < ntiles) {
+      const uint32_t kw = __shfl_sync(L3D_FULL_MASK, (uint32_t)(best >> 32), k - 1);
+      kth = f32_unorder(kw);
+      base = k;
+    }
+  }
+
+  if (overflow) knn_row_slow<MODE>(p, packed, q, row, lane);
+  else knn_store_packed(p, row, lane, best);
+}
+
+// R consecutive rows per warp: every candidate float4 is loaded from shared memory ONCE and used
+// for R queries.  The second ncu capture showed the shared-memory/shuffle (MIO) pipe at 74 % with
+// 128 of ~220 wavefronts per row being candidate loads: R = 2 halves them and doubles the ILP of
+// the (shuffle-latency-bound) sorting networks.
+template <int MODE, int R>
+__device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __restrict__ packed,
+                                            unsigned long long* __restrict__ cbuf, const float4 (&q)[R],
+                                            long row0, int ntiles, int lane) {
+  constexpr int CAP = 64;
+  const int k = p.k;
+  int base[R];
+  float kth[R];
+  bool ovf[R];
+  unsigned long long best[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { base[r] = 0; kth[r] = -INFINITY; ovf[r] = (p.force_slow != 0); best[r] = 0ull; }
+
+  for (int t = 0; t < ntiles; ++t) {
+    float d[R][32];
+    const float4* pt = packed + t * KNN_TILE + lane;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float4 c = pt[e * 32];
+#pragma unroll
+      for (int r = 0; r < R; ++r) d[r][e] = knn_key<MODE>(q[r], c);
+    }
+    float mx[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float m = d[r][0];
+#pragma unroll
+      for (int e = 1; e < 32; ++e) m = fmaxf(m, d[r][e]);
+      mx[r] = warp_sort32_keys_desc(m, lane);
+    }
+    uint32_t mask[R];
+    int cnt[R], incl[R], total[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float thr = fmaxf(__shfl_sync(L3D_FULL_MASK, mx[r], k - 1), kth[r]);
+      uint32_t mk = 0u;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mk |= (d[r][e] >= thr) ? (1u << e) : 0u;
+      mask[r] = mk;
+      cnt[r] = __popc(mk);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) incl[r] = warp_inclusive_scan(cnt[r], lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      total[r] = __shfl_sync(L3D_FULL_MASK, incl[r], 31);
+      if (base[r] + total[r] > CAP) ovf[r] = true;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (ovf[r]) continue;
+      unsigned long long* cb = cbuf + r * CAP;
+      if (base[r] && lane < base[r]) cb[lane] = best[r];
+      int off = base[r] + incl[r] - cnt[r];
+      uint32_t mk = mask[r];
+      while (mk) {
+        const int e = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const int j = t * KNN_TILE + e * 32 + lane;
+        cb[off++] = pack_pair(knn_key<MODE>(q[r], packed[j]), (uint32_t)j);
+      }
+    }
+    __syncwarp();
+    // first 32 survivors of every row: one straight-line network over all R rows (the exchanges of
+    // different rows are independent, so their shuffle latencies overlap)
+    unsigned long long a[R];
+    int n_in[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      n_in[r] = base[r] + total[r];
+      a[r] = (lane < n_in[r]) ? cbuf[r * CAP + lane] : 0ull;
+    }
+    warp_sort32_desc_x<R>(a, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (n_in[r] > 32 && !ovf[r]) {
+        // survivors 32..63: sort them too, pair a[i] with b[31-i], keep the better 32, clean up
+        unsigned long long b = (lane + 32 < n_in[r]) ? cbuf[r * CAP + lane + 32] : 0ull;
+        b = shfl_xor_u64(warp_sort32_desc(b, lane), 31);
+        unsigned long long c = (b > a[r]) ? b : a[r];
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) c = cmpx_u64(c, j, (lane & j) == 0);
+        a[r] = c;
+      }
+      best[r] = a[r];
+      if (t + 1 < ntiles) {
+        kth[r] = f32_unorder(__shfl_sync(L3D_FULL_MASK, (uint32_t)(best[r] >> 32), k - 1));
+        base[r] = k;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (ovf[r]) knn_row_slow<MODE>(p, packed, q[r], row0 + r, lane);
+    else knn_store_packed(p, row0 + r, lane, best[r]);
+  }
+}
+
 // Dynamic shared memory layout (bytes):
 //   [0,16)                       mbarrier
 //   [16, 16 + 12*KNN_CHUNK)      raw staging chunk (3 * KNN_CHUNK floats)
 //   [.., + 16*NPAD)              packed candidates (float4), NPAD = N rounded up to KNN_TILE
 //   [.., + KNN_WARPS*CAP*8)      per-warp survivor buffers
+// survivor-buffer entries per warp: KS = 1 runs KNN_R rows per warp, 64 entries each
+#define KNN_CBUF(KS) ((KS) == 1 ? 64 * KNN_R : 64 * (KS))
 __host__ __device__ inline size_t knn_smem_bytes(int N, int KS) {
   const size_t npad = (size_t)((N + KNN_TILE - 1) / KNN_TILE) * KNN_TILE;
-  return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad + (size_t)KNN_WARPS * 64 * KS * 8;
+  return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad + (size_t)KNN_WARPS * KNN_CBUF(KS) * 8;
 }
 
 template <int MODE, int KS, bool SELF, bool CAND_BCN>
-__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnParams p) {
+__global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float* stage = reinterpret_cast<float*>(smem + 16);
@@ -295,7 +494,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnParams p) {
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  uint2* cbuf = cbuf_all + warp * (64 * KS);
+  uint2* cbuf = cbuf_all + warp * KNN_CBUF(KS);
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -353,16 +552,31 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnParams p) {
     __syncthreads();
 
     // ---- rows of this segment, one warp each ---------------------------------------
-    for (long row = seg + warp; row < seg_end; row += KNN_WARPS) {
-      float4 q;
-      if (SELF) {
-        q = packed[(int)(row - (long)b * M)];
-      } else {
-        const float* qp = p.query + row * 3;
-        q = knn_pack<MODE>(qp[0], qp[1], qp[2]);
+    auto load_query = [&](long row) -> float4 {
+      if (SELF) return packed[(int)(row - (long)b * M)];
+      const float* qp = p.query + row * 3;
+      return knn_pack<MODE>(qp[0], qp[1], qp[2]);
+    };
+    if (KS == 1 && !(p.full_sort && !p.force_slow)) {
+      // KNN_R consecutive rows per warp; a ragged tail falls back to one row at a time
+      unsigned long long* cb = reinterpret_cast<unsigned long long*>(cbuf);
+      long row = seg + (long)warp * KNN_R;
+      for (; row + KNN_R <= seg_end; row += (long)KNN_WARPS * KNN_R) {
+        float4 q[KNN_R];
+#pragma unroll
+        for (int r = 0; r < KNN_R; ++r) q[r] = load_query(row + r);
+        knn_rows_v2<MODE, KNN_R>(p, packed, cb, q, row, ntiles, lane);
       }
-      if (KS == 1 && p.full_sort && !p.force_slow) knn_row_sort<MODE>(p, packed, q, row, lane);
-      else knn_row<MODE, KS>(p, packed, cbuf, q, row, ntiles, lane);
+      for (; row < seg_end; ++row) {
+        const float4 q1[1] = {load_query(row)};
+        knn_rows_v2<MODE, 1>(p, packed, cb, q1, row, ntiles, lane);
+      }
+    } else {
+      for (long row = seg + warp; row < seg_end; row += KNN_WARPS) {
+        const float4 q = load_query(row);
+        if (KS == 1) knn_row_sort<MODE>(p, packed, q, row, lane);
+        else knn_row<MODE, KS>(p, packed, cbuf, q, row, ntiles, lane);
+      }
     }
     seg = seg_end;
     __syncthreads();  // all warps done with packed[] before the next cloud is staged

@@ -197,6 +197,18 @@ def test_knn_point_family(oracle_mod, golden_dir):
         np.sort(oracle_mod.knn_sqdist(g["data"], g["query"], 16), -1), np.sort(g["pc_idx"], -1))
 
 
+def test_host_buffer_entry_point(oracle_mod):
+    """l3d_knn_expansion_host: HOST buffers in/out (pageable and pinned), sliced + overlapped internally."""
+    from learning3d_b200 import _C
+    for B in (1, 3, 32):
+        x = torch.rand(B, 3, 1024)
+        idx = torch.empty(B, 1024, 20, dtype=torch.int64)
+        if B == 32:
+            x, idx = x.pin_memory(), idx.pin_memory()
+        _C.check(_C.lib().l3d_knn_expansion_host(_C._P(x.data_ptr()), B, 1024, 20, _C._P(idx.data_ptr())))
+        assert np.array_equal(idx.numpy(), oracle_mod.knn_expansion(x.numpy(), 20, mt=True))
+
+
 def test_error_codes():
     from learning3d_b200 import _C
     from learning3d_b200.utils import knn
