@@ -405,9 +405,14 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float thr = fmaxf(__shfl_sync(L3D_FULL_MASK, mx[r], k - 1), kth[r]);
-      uint32_t mk = 0u;
+      // survivor mask: bit e = (d[e] >= thr).  d - thr is +0 on equality, so the survivors are the
+      // differences with a clear sign bit; one FADD (FMA pipe) + one funnel shift (ALU pipe) per key
+      // instead of FSETP + predicated OR (two ALU-pipe instructions; the ALU pipe is the busier one).
+      uint32_t neg = 0u;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) mk |= (d[r][e] >= thr) ? (1u << e) : 0u;
+      for (int e = 31; e >= 0; --e)
+        neg = __funnelshift_l(__float_as_uint(__fsub_rn(d[r][e], thr)), neg, 1);
+      const uint32_t mk = ~neg;
       mask[r] = mk;
       cnt[r] = __popc(mk);
     }

@@ -1,0 +1,150 @@
+"""FlowNet3D on the pointnet2 drop-in ops.  Same module tree / parameter names as
+learning3d/models/flownet3d.py:73-328 (sa1..sa4, fe_layer, su1..su3, fp, conv1, bn1, conv2), so a
+reference checkpoint loads; every grouping call site of the reference (:110-114 FPS+gather+ball
+query+group, :157-174 kNN flow embedding, :222-230 kNN up-conv, :272-276 3-NN interpolation) goes through
+learning3d_b200.utils.lib.pointnet2_utils."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..utils.lib import pointnet2_utils as pointutils
+
+
+def _mlp2d(channels):
+    convs, bns = nn.ModuleList(), nn.ModuleList()
+    for c_in, c_out in zip(channels[:-1], channels[1:]):
+        convs.append(nn.Conv2d(c_in, c_out, 1, bias=False))
+        bns.append(nn.BatchNorm2d(c_out))
+    return convs, bns
+
+
+class PointNetSetAbstraction(nn.Module):
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs, self.mlp_bns = _mlp2d([in_channel + 3] + list(mlp))
+        self.queryandgroup = pointutils.GroupAll() if group_all else pointutils.QueryAndGroup(radius, nsample)
+
+    def forward(self, xyz, points):
+        """xyz [B,3,N], points [B,D,N] -> (new_xyz [B,3,S], new_points [B,D',S])."""
+        xyz_t = xyz.permute(0, 2, 1).contiguous()
+        if self.group_all:
+            new_xyz = xyz
+        else:
+            fps_idx = pointutils.furthest_point_sample(xyz_t, self.npoint)
+            new_xyz = pointutils.gather_operation(xyz.contiguous(), fps_idx)
+        feats = self.queryandgroup(xyz_t, new_xyz.transpose(2, 1).contiguous(), points)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            feats = F.relu(bn(conv(feats)))
+        return new_xyz, torch.max(feats, -1)[0]
+
+
+class FlowEmbedding(nn.Module):
+    def __init__(self, radius, nsample, in_channel, mlp, pooling='max', corr_func='concat', knn=True):
+        super().__init__()
+        if not knn or corr_func != 'concat':
+            raise NotImplementedError("only the configuration FlowNet3D uses (knn=True, corr_func='concat')")
+        self.radius, self.nsample, self.knn, self.pooling, self.corr_func = radius, nsample, knn, pooling, corr_func
+        self.mlp_convs, self.mlp_bns = _mlp2d([in_channel * 2 + 3] + list(mlp))
+
+    def forward(self, pos1, pos2, feature1, feature2):
+        B, _, N = pos1.shape
+        _, idx = pointutils.knn(self.nsample, pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
+        pos_diff = pointutils.grouping_operation(pos2.contiguous(), idx) - pos1.view(B, -1, N, 1)
+        feat2_grouped = pointutils.grouping_operation(feature2.contiguous(), idx)
+        feat = torch.cat([pos_diff, feat2_grouped,
+                          feature1.view(B, -1, N, 1).repeat(1, 1, 1, self.nsample)], dim=1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            feat = F.relu(bn(conv(feat)))
+        return pos1, torch.max(feat, -1)[0]
+
+
+class PointNetSetUpConv(nn.Module):
+    def __init__(self, nsample, radius, f1_channel, f2_channel, mlp, mlp2, knn=True):
+        super().__init__()
+        if not knn:
+            raise NotImplementedError("FlowNet3D uses knn=True")
+        self.nsample, self.radius, self.knn = nsample, radius, knn
+        self.mlp1_convs, self.mlp2_convs = nn.ModuleList(), nn.ModuleList()
+        last = f2_channel + 3
+        for c_out in mlp:
+            self.mlp1_convs.append(nn.Sequential(nn.Conv2d(last, c_out, 1, bias=False), nn.BatchNorm2d(c_out),
+                                                 nn.ReLU(inplace=False)))
+            last = c_out
+        last = (mlp[-1] if len(mlp) != 0 else last) + f1_channel
+        for c_out in mlp2:
+            self.mlp2_convs.append(nn.Sequential(nn.Conv1d(last, c_out, 1, bias=False), nn.BatchNorm1d(c_out),
+                                                 nn.ReLU(inplace=False)))
+            last = c_out
+
+    def forward(self, pos1, pos2, feature1, feature2):
+        B, _, N = pos1.shape
+        _, idx = pointutils.knn(self.nsample, pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
+        pos_diff = pointutils.grouping_operation(pos2.contiguous(), idx) - pos1.view(B, -1, N, 1)
+        feat = torch.cat([pointutils.grouping_operation(feature2.contiguous(), idx), pos_diff], dim=1)
+        for conv in self.mlp1_convs:
+            feat = conv(feat)
+        feat = feat.max(-1)[0]
+        if feature1 is not None:
+            feat = torch.cat([feat, feature1], dim=1)
+        for conv in self.mlp2_convs:
+            feat = conv(feat)
+        return feat
+
+
+class PointNetFeaturePropogation(nn.Module):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for c_out in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, c_out, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(c_out))
+            last = c_out
+
+    def forward(self, pos1, pos2, feature1, feature2):
+        B, _, N = pos1.shape
+        dists, idx = pointutils.three_nn(pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
+        dists = dists.clamp_min(1e-10)                      # dists[dists < 1e-10] = 1e-10
+        weight = 1.0 / dists
+        weight = weight / torch.sum(weight, -1, keepdim=True)
+        grouped = pointutils.grouping_operation(feature2.contiguous(), idx)
+        feat = torch.sum(grouped * weight.view(B, 1, N, 3), dim=-1)
+        if feature1 is not None:
+            feat = torch.cat([feat, feature1], 1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            feat = F.relu(bn(conv(feat)))
+        return feat
+
+
+class FlowNet3D(nn.Module):
+    def __init__(self):
+        super().__init__()
+        SA = PointNetSetAbstraction
+        self.sa1 = SA(1024, 0.5, 16, 3, [32, 32, 64], False)
+        self.sa2 = SA(256, 1.0, 16, 64, [64, 64, 128], False)
+        self.sa3 = SA(64, 2.0, 8, 128, [128, 128, 256], False)
+        self.sa4 = SA(16, 4.0, 8, 256, [256, 256, 512], False)
+        self.fe_layer = FlowEmbedding(10.0, 64, 128, [128, 128, 128], pooling='max', corr_func='concat')
+        self.su1 = PointNetSetUpConv(8, 2.4, 256, 512, [], [256, 256])
+        self.su2 = PointNetSetUpConv(8, 1.2, 128 + 128, 256, [128, 128, 256], [256])
+        self.su3 = PointNetSetUpConv(8, 0.6, 64, 256, [128, 128, 256], [256])
+        self.fp = PointNetFeaturePropogation(256 + 3, [256, 256])
+        self.conv1 = nn.Conv1d(256, 128, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.conv2 = nn.Conv1d(128, 3, kernel_size=1, bias=True)
+
+    def forward(self, pc1, pc2, feature1, feature2):
+        l1_pc1, l1_f1 = self.sa1(pc1, feature1)
+        l2_pc1, l2_f1 = self.sa2(l1_pc1, l1_f1)
+        l1_pc2, l1_f2 = self.sa1(pc2, feature2)
+        l2_pc2, l2_f2 = self.sa2(l1_pc2, l1_f2)
+        _, l2_f1_new = self.fe_layer(l2_pc1, l2_pc2, l2_f1, l2_f2)
+        l3_pc1, l3_f1 = self.sa3(l2_pc1, l2_f1_new)
+        l4_pc1, l4_f1 = self.sa4(l3_pc1, l3_f1)
+        l3_fnew1 = self.su1(l3_pc1, l4_pc1, l3_f1, l4_f1)
+        l2_fnew1 = self.su2(l2_pc1, l3_pc1, torch.cat([l2_f1, l2_f1_new], dim=1), l3_fnew1)
+        l1_fnew1 = self.su3(l1_pc1, l2_pc1, l1_f1, l2_fnew1)
+        l0_fnew1 = self.fp(pc1, l1_pc1, feature1, l1_fnew1)
+        x = F.relu(self.bn1(self.conv1(l0_fnew1)))
+        return self.conv2(x)

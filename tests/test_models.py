@@ -1,0 +1,63 @@
+"""Callers of the hot path (API-compat): state_dict compatibility with the reference's checkpoints (CPU, only
+where /root/reference exists) and GPU forward checks."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference/pretrained"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkpoints only exist in the build container")
+def test_reference_checkpoints_load():
+    from learning3d_b200.models import DGCNN, FlowNet3D
+    sd = torch.load(f"{REF}/exp_flownet/models/model.best.t7", map_location="cpu", weights_only=False)
+    FlowNet3D().load_state_dict(sd, strict=True)                   # identical module tree / names
+    dcp = torch.load(f"{REF}/exp_dcp/models/best_model.t7", map_location="cpu", weights_only=False)
+    emb = {k[len("emb_nn."):]: v for k, v in dcp.items() if k.startswith("emb_nn.")}
+    DGCNN(emb_dims=512).load_state_dict(emb, strict=True)
+    from learning3d_b200.utils import SVDHead
+    SVDHead(512).load_state_dict({"reflect": dcp["head.reflect"]}, strict=True)
+
+
+@pytest.mark.gpu
+def test_dgcnn_forward_matches_torch_graph():
+    from learning3d_b200.models import DGCNN
+    from oracle import ref_torch
+    torch.manual_seed(0)
+    net = DGCNN(emb_dims=256).cuda().eval()
+    x = torch.rand(4, 1024, 3, device="cuda")
+    with torch.no_grad():
+        y = net(x)
+        # same weights on the reference's own graph construction (matmul + topk + gather)
+        g = ref_torch.get_graph_feature(x.permute(0, 2, 1).contiguous(), k=20)
+        h = g
+        pooled = []
+        for i in range(1, 5):
+            h = torch.relu(getattr(net, f"bn{i}")(getattr(net, f"conv{i}")(h)))
+            pooled.append(h.max(dim=-1, keepdim=True)[0])
+        want = torch.relu(net.bn5(net.conv5(torch.cat(pooled, 1)))).view(4, -1, 1024)
+    assert y.shape == (4, 256, 1024)
+    # identical graphs except rows with exact key ties (topk order unspecified) -> tiny fraction of points
+    frac_same = (y == want).all(1).float().mean().item()
+    assert frac_same > 0.995
+    assert torch.allclose(y, want, atol=1e-4) or frac_same > 0.995
+
+
+@pytest.mark.gpu
+def test_flownet3d_forward_runs_on_dropin_ops():
+    from learning3d_b200.models import FlowNet3D
+    torch.manual_seed(1)
+    net = FlowNet3D().cuda().eval()
+    pc1 = (torch.rand(2, 3, 2048, device="cuda") * 4 - 2)
+    pc2 = pc1 + 0.05 * torch.randn_like(pc1)
+    with torch.no_grad():
+        flow = net(pc1, pc2, pc1.clone(), pc2.clone())
+    assert flow.shape == (2, 3, 2048) and torch.isfinite(flow).all()
+    # training-mode backward through gather / group ops
+    net.train()
+    out = net(pc1, pc2, pc1.clone(), pc2.clone())
+    out.square().mean().backward()
+    g = net.sa1.mlp_convs[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
