@@ -39,10 +39,11 @@ def test_dgcnn_forward_matches_torch_graph():
             pooled.append(h.max(dim=-1, keepdim=True)[0])
         want = torch.relu(net.bn5(net.conv5(torch.cat(pooled, 1)))).view(4, -1, 1024)
     assert y.shape == (4, 256, 1024)
-    # identical graphs except rows with exact key ties (topk order unspecified) -> tiny fraction of points
-    frac_same = (y == want).all(1).float().mean().item()
-    assert frac_same > 0.995
-    assert torch.allclose(y, want, atol=1e-4) or frac_same > 0.995
+    # Same graph except rows with exact key ties (topk order unspecified); the conv stack sees a
+    # contiguous tensor here and a permuted view there, so cuDNN may pick different kernels: compare
+    # to a tolerance, per point.
+    close = ((y - want).abs() <= 1e-4 + 1e-4 * want.abs()).all(1)
+    assert close.float().mean().item() > 0.995
 
 
 @pytest.mark.gpu
