@@ -23,27 +23,31 @@ def test_reference_checkpoints_load():
 
 @pytest.mark.gpu
 def test_dgcnn_forward_matches_torch_graph():
+    """DGCNN = get_graph_feature (ours) + a torch conv stack (as in the reference).  The graph feature must
+    equal the reference's matmul+topk+gather construction row for row (rows with an exact key tie aside:
+    topk's tie order is unspecified); the forward must then agree to conv tolerance."""
     from learning3d_b200.models import DGCNN
+    from learning3d_b200.utils import get_graph_feature
     from oracle import ref_torch
     torch.manual_seed(0)
     net = DGCNN(emb_dims=256).cuda().eval()
     x = torch.rand(4, 1024, 3, device="cuda")
+    xt = x.permute(0, 2, 1).contiguous()
     with torch.no_grad():
         y = net(x)
-        # same weights on the reference's own graph construction (matmul + topk + gather)
-        g = ref_torch.get_graph_feature(x.permute(0, 2, 1).contiguous(), k=20)
-        h = g
-        pooled = []
+        g_ref = ref_torch.get_graph_feature(xt, k=20).contiguous()
+        g_our = get_graph_feature(xt, k=20)
+        same_rows = (g_ref == g_our).all(1).all(-1)                       # [B, N]
+        assert same_rows.float().mean().item() > 0.999
+        h, pooled = g_ref, []
         for i in range(1, 5):
             h = torch.relu(getattr(net, f"bn{i}")(getattr(net, f"conv{i}")(h)))
             pooled.append(h.max(dim=-1, keepdim=True)[0])
         want = torch.relu(net.bn5(net.conv5(torch.cat(pooled, 1)))).view(4, -1, 1024)
-    assert y.shape == (4, 256, 1024)
-    # Same graph except rows with exact key ties (topk order unspecified); the conv stack sees a
-    # contiguous tensor here and a permuted view there, so cuDNN may pick different kernels: compare
-    # to a tolerance, per point.
-    close = ((y - want).abs() <= 1e-4 + 1e-4 * want.abs()).all(1)
-    assert close.float().mean().item() > 0.995
+    assert y.shape == (4, 256, 1024) and torch.isfinite(y).all()
+    rel = (y - want).abs().max().item() / max(want.abs().max().item(), 1e-6)
+    print("DGCNN forward max rel diff vs reference graph:", rel)
+    assert rel < 2e-2      # tie rows can move a neighbour; everything else agrees to conv rounding
 
 
 @pytest.mark.gpu
