@@ -606,11 +606,21 @@ template <int MODE, int KS, bool SELF, bool CAND_BCN>
 static int knn_launch_t(KnnParams p, cudaStream_t stream) {
   auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN>;
   const size_t smem = knn_smem_bytes(p.N, KS);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, KNN_THREADS, smem);
-  if (e != cudaSuccess) return (int)e;
+  // the function attribute and the occupancy query are host-side driver calls (~5 us together):
+  // cache them per (instantiation, device, smem size) so that a steady-state call is just the launch
+  static thread_local int c_dev = -1, c_occ = 0;
+  static thread_local size_t c_smem = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != c_dev || smem != c_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, KNN_THREADS, smem);
+    if (e != cudaSuccess) return (int)e;
+    c_dev = dev; c_smem = smem; c_occ = o;
+  }
+  int occ = c_occ;
   if (occ < 1) return L3D_ERR_UNSUPPORTED;
   if (occ > 4) occ = 4;
   const long rows = (long)p.B * p.M;
