@@ -113,5 +113,23 @@ def require_cuda(t, name, dtype=torch.float32):
     return t.contiguous()
 
 
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(dev):
+    """Context that makes `dev` current; free when it already is (torch.cuda.device costs ~10 us)."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(dev)
+
+
 def launch_count():
     return int(lib().l3d_launch_count())

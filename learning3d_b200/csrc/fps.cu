@@ -53,9 +53,7 @@ __device__ __forceinline__ bool fps_better(float av, uint32_t at, float bv, uint
 
 template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
-  __shared__ float s_v[2][FPS_WARPS];
-  __shared__ uint32_t s_t[2][FPS_WARPS];
-  __shared__ int s_k[2][FPS_WARPS];
+  __shared__ uint2 s_r[2][FPS_WARPS];   // per-warp (max distance bits, ~tiekey), double-buffered
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -82,7 +80,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
       }
     } else {
       px[i] = py[i] = pz[i] = 0.f;
-      td[i] = -1.f;            // never selected (distances are >= 0)
+      td[i] = 0.f;             // padding: smallest distance and the worst tie key -> never preferred
       tk[i] = 0xffffffffu;
     }
   }
@@ -95,9 +93,10 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
 
   for (int j = 1; j < M; ++j) {
     const float cx = __ldg(xyz + old * 3), cy = __ldg(xyz + old * 3 + 1), cz = __ldg(xyz + old * 3 + 2);
-    float bv = -2.f;
-    uint32_t bt = 0xffffffffu;
-    int bk = 0;
+    // Distances are >= +0, so their bit patterns order like unsigned integers: the arg-max is two
+    // hardware warp reductions (REDUX.MAX.U32) — first the distance bits, then ~tiekey among the
+    // lanes that hold the maximum — instead of a 5-step shuffle butterfly over three values.
+    uint32_t bv = 0u, bt = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
       const int k = tid + i * FPS_THREADS;
@@ -105,30 +104,25 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
         const float d = fps_dist(p.mode, px[i], py[i], pz[i], cx, cy, cz);
         td[i] = fminf(d, td[i]);          // d2 = min(d, temp[k])  /  distance[mask] = dist[mask]
       }
-      if (fps_better(td[i], tk[i], bv, bt)) { bv = td[i]; bt = tk[i]; bk = k; }
+      const uint32_t u = __float_as_uint(td[i]);
+      if (u > bv || (u == bv && tk[i] < bt)) { bv = u; bt = tk[i]; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(L3D_FULL_MASK, bv, o);
-      const uint32_t ot = __shfl_xor_sync(L3D_FULL_MASK, bt, o);
-      const int ok = __shfl_xor_sync(L3D_FULL_MASK, bk, o);
-      if (fps_better(ov, ot, bv, bt)) { bv = ov; bt = ot; bk = ok; }
-    }
+    uint32_t wv = __reduce_max_sync(L3D_FULL_MASK, bv);
+    uint32_t wc = __reduce_max_sync(L3D_FULL_MASK, (bv == wv) ? ~bt : 0u);
     const int buf = j & 1;
-    if (lane == 0) { s_v[buf][warp] = bv; s_t[buf][warp] = bt; s_k[buf][warp] = bk; }
+    if (lane == 0) s_r[buf][warp] = make_uint2(wv, wc);
     __syncthreads();
     // every warp reduces the FPS_WARPS partial winners redundantly: no second barrier
-    bv = (lane < FPS_WARPS) ? s_v[buf][lane] : -2.f;
-    bt = (lane < FPS_WARPS) ? s_t[buf][lane] : 0xffffffffu;
-    bk = (lane < FPS_WARPS) ? s_k[buf][lane] : 0;
-#pragma unroll
-    for (int o = FPS_WARPS / 2; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(L3D_FULL_MASK, bv, o);
-      const uint32_t ot = __shfl_xor_sync(L3D_FULL_MASK, bt, o);
-      const int ok = __shfl_xor_sync(L3D_FULL_MASK, bk, o);
-      if (fps_better(ov, ot, bv, bt)) { bv = ov; bt = ot; bk = ok; }
+    const uint2 e = (lane < FPS_WARPS) ? s_r[buf][lane] : make_uint2(0u, 0u);
+    wv = __reduce_max_sync(L3D_FULL_MASK, e.x);
+    wc = __reduce_max_sync(L3D_FULL_MASK, (e.x == wv) ? e.y : 0u);
+    const uint32_t wtk = ~wc;
+    if (p.mode == 0) {
+      const uint32_t r = (p.ref_log2 == 0) ? 0u : (__brev(wtk >> 16) >> (32 - p.ref_log2));
+      old = (int)((wtk & 0xffffu) * (uint32_t)p.ref_bs + r);
+    } else {
+      old = (int)wtk;
     }
-    old = __shfl_sync(L3D_FULL_MASK, bk, 0);
     if (tid == 0) {
       if (p.idx64) reinterpret_cast<long long*>(p.out)[(size_t)b * M + j] = old;
       else reinterpret_cast<int*>(p.out)[(size_t)b * M + j] = old;

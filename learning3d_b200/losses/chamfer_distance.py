@@ -44,31 +44,35 @@ class _ChamferLoss(torch.autograd.Function):
         B, n, _ = xyz1.shape
         m = xyz2.shape[1]
         dev = xyz1.device
-        dist = torch.empty(B * (n + m), device=dev)
-        idx = torch.empty(B * (n + m), dtype=torch.int, device=dev)
-        loss = torch.empty((), device=dev)
+        tot = B * (n + m)
+        buf = torch.empty(2 * tot + 1, device=dev)          # [dist | idx (int32 bits) | loss]
+        dist, idx, loss = buf, buf, buf[2 * tot]
+        dptr = buf.data_ptr()
         lib = _C.lib()
-        with torch.cuda.device(dev):
+        with _C.on_device(dev):
             ws = _workspace(dev, int(lib.l3d_chamfer_ws_bytes(B, n, m)))
             _C.check(lib.l3d_chamfer_loss_forward(
-                _C.ptr(xyz1), _C.ptr(xyz2), B, n, m, _C.ptr(dist), _C._P(dist.data_ptr() + 4 * B * n),
-                _C.ptr(idx), _C._P(idx.data_ptr() + 4 * B * n), _C.ptr(loss), _C.ptr(ws),
+                _C.ptr(xyz1), _C.ptr(xyz2), B, n, m, _C._P(dptr), _C._P(dptr + 4 * B * n),
+                _C._P(dptr + 4 * tot), _C._P(dptr + 4 * (tot + B * n)), _C._P(dptr + 8 * tot), _C.ptr(ws),
                 _C.stream()), "chamfer loss forward")
-        ctx.save_for_backward(xyz1, xyz2, dist, idx)
+        ctx.save_for_backward(xyz1, xyz2, buf)
         return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        xyz1, xyz2, dist, idx = ctx.saved_tensors
+        xyz1, xyz2, buf = ctx.saved_tensors
         B, n, _ = xyz1.shape
         m = xyz2.shape[1]
-        grad_loss = grad_loss.contiguous().to(torch.float32)
+        tot = B * (n + m)
+        dptr = buf.data_ptr()
+        if grad_loss.dtype != torch.float32 or not grad_loss.is_contiguous():
+            grad_loss = grad_loss.contiguous().to(torch.float32)
         g1 = torch.empty_like(xyz1)
         g2 = torch.empty_like(xyz2)
-        with torch.cuda.device(xyz1.device):
+        with _C.on_device(xyz1.device):
             _C.check(_C.lib().l3d_chamfer_loss_backward(
-                _C.ptr(xyz1), _C.ptr(xyz2), B, n, m, _C.ptr(dist), _C._P(dist.data_ptr() + 4 * B * n),
-                _C.ptr(idx), _C._P(idx.data_ptr() + 4 * B * n), _C.ptr(grad_loss), _C.ptr(g1),
+                _C.ptr(xyz1), _C.ptr(xyz2), B, n, m, _C._P(dptr), _C._P(dptr + 4 * B * n),
+                _C._P(dptr + 4 * tot), _C._P(dptr + 4 * (tot + B * n)), _C.ptr(grad_loss), _C.ptr(g1),
                 _C.ptr(g2), _C.stream()), "chamfer loss backward")
         return g1, g2
 

@@ -21,7 +21,7 @@ class ChamferDistanceFunction(torch.autograd.Function):
         dist2 = torch.empty(batchsize, m, device=dev)
         idx1 = torch.empty(batchsize, n, dtype=torch.int, device=dev)
         idx2 = torch.empty(batchsize, m, dtype=torch.int, device=dev)
-        with torch.cuda.device(dev):
+        with _C.on_device(dev):
             _C.check(_C.lib().l3d_chamfer_forward(_C.ptr(xyz1), _C.ptr(xyz2), batchsize, n, m,
                                                   _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1),
                                                   _C.ptr(idx2), _C.stream()), "chamfer forward")
@@ -37,7 +37,7 @@ class ChamferDistanceFunction(torch.autograd.Function):
         m = xyz2.size(1)
         gradxyz1 = torch.empty_like(xyz1)
         gradxyz2 = torch.empty_like(xyz2)
-        with torch.cuda.device(xyz1.device):
+        with _C.on_device(xyz1.device):
             _C.check(_C.lib().l3d_chamfer_backward(
                 _C.ptr(xyz1), _C.ptr(xyz2), batchsize, n, m, _C.ptr(graddist1), _C.ptr(graddist2),
                 _C.ptr(idx1), _C.ptr(idx2), _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.stream()),

@@ -34,7 +34,7 @@ class EMDFunction(torch.autograd.Function):
         lib = _C.lib()
         cost = torch.empty((B,), dtype=torch.float32, device=dev)
         match = torch.empty((B, n, m), dtype=torch.float32, device=dev)     # emd.cu:18
-        with torch.cuda.device(dev):
+        with _C.on_device(dev):
             ws = _ws(dev, lib.l3d_emd_forward_ws_bytes(B, n, m))
             _C.check(lib.l3d_emd_forward(_C.ptr(xyz1), _C.ptr(xyz2), B, n, m, _C.ptr(cost),
                                          _C.ptr(match), _C.ptr(ws), _C.stream()), "emd_forward")
@@ -50,7 +50,7 @@ class EMDFunction(torch.autograd.Function):
         lib = _C.lib()
         g1 = torch.empty_like(xyz1)
         g2 = torch.empty_like(xyz2)
-        with torch.cuda.device(xyz1.device):
+        with _C.on_device(xyz1.device):
             ws = _ws(xyz1.device, lib.l3d_emd_backward_ws_bytes(B, n, m))
             _C.check(lib.l3d_emd_backward(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(match), B, n, m,
                                           _C.ptr(g1), _C.ptr(g2), _C.ptr(ws), _C.stream()), "emd_backward")

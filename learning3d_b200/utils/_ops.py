@@ -21,7 +21,7 @@ def square_distance(src, dst):
     B, N, _ = src.shape
     M = dst.shape[1]
     out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
+    with _C.on_device(src.device):
         _C.check(_C.lib().l3d_square_distance(_C.ptr(src), _C.ptr(dst), B, N, M, _C.ptr(out),
                                               _C.stream()), "square_distance")
     return out
@@ -33,7 +33,7 @@ class _IndexPoints(torch.autograd.Function):
         B, N, C = points.shape
         R = idx.numel() // B if B > 0 else 0
         out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=points.device)
-        with torch.cuda.device(points.device):
+        with _C.on_device(points.device):
             _C.check(_C.lib().l3d_index_points(_C.ptr(points), _C.ptr(idx), B, N, R, C, _C.ptr(out),
                                                _C.stream()), "index_points")
         ctx.save_for_backward(idx)
@@ -46,7 +46,7 @@ class _IndexPoints(torch.autograd.Function):
         B, N, C, R = ctx.dims
         grad_out = grad_out.contiguous()
         gp = torch.zeros((B, N, C), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _C.on_device(grad_out.device):
             _C.check(_C.lib().l3d_index_points_grad(_C.ptr(grad_out), _C.ptr(idx), B, N, R, C,
                                                     _C.ptr(gp), _C.stream()), "index_points backward")
         return gp, None
@@ -68,7 +68,7 @@ def farthest_point_sample(xyz, npoint, start=None):
     cent = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
     if start is not None:
         start = start.to(device=xyz.device, dtype=torch.int64).contiguous()
-    with torch.cuda.device(xyz.device):
+    with _C.on_device(xyz.device):
         _C.check(_C.lib().l3d_farthest_point_sample(_C.ptr(xyz), B, N, npoint, _C.ptr(start),
                                                     _C.ptr(cent), _C.stream()), "farthest_point_sample")
     return cent
@@ -84,7 +84,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz, itself_indices=None, get_cnt
         itself_indices = itself_indices.to(device=xyz.device, dtype=torch.int64).contiguous()
     # `sqrdists > radius ** 2`: python computes radius**2 in double, the comparison casts it to fp32
     r2 = float(np.float32(radius ** 2))
-    with torch.cuda.device(xyz.device):
+    with _C.on_device(xyz.device):
         _C.check(_C.lib().l3d_query_ball_point(_C.ptr(xyz), _C.ptr(new_xyz), B, N, S, r2, nsample,
                                                _C.ptr(itself_indices), _C.ptr(idx), _C.ptr(cnt),
                                                _C.stream()), "query_ball_point")
@@ -99,7 +99,7 @@ def knn_sqdist(nsample, xyz, new_xyz):
     if nsample > N:
         raise RuntimeError("selected index k out of range")
     idx = torch.empty((B, S, nsample), dtype=torch.int64, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _C.on_device(xyz.device):
         _C.check(_C.lib().l3d_knn_sqdist(_C.ptr(xyz), _C.ptr(new_xyz), B, N, S, nsample, _C.ptr(idx),
                                          _C.stream()), "knn_point")
     return idx
@@ -112,7 +112,7 @@ def compute_density(xyz, bandwidth):
     out = torch.empty((B, N), dtype=torch.float32, device=xyz.device)
     two_bw2 = float(np.float32(2.0 * bandwidth * bandwidth))
     norm = float(np.float32(2.5 * bandwidth))
-    with torch.cuda.device(xyz.device):
+    with _C.on_device(xyz.device):
         _C.check(_C.lib().l3d_compute_density(_C.ptr(xyz), B, N, two_bw2, norm, _C.ptr(out),
                                               _C.stream()), "compute_density")
     return out

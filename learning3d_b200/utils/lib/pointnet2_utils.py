@@ -34,7 +34,7 @@ class FurthestPointSampling(Function):
         B, N, _ = xyz.size()
         output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
         temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
+        with _C.on_device(xyz.device):
             _C.check(_C.lib().l3d_pn2_furthest_point_sampling(B, N, npoint, _C.ptr(xyz), _C.ptr(temp),
                                                               _C.ptr(output), _C.stream()),
                      "furthest_point_sample")
@@ -60,7 +60,7 @@ class GatherOperation(Function):
         B, npoint = idx.size()
         _, C, N = features.size()
         output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _C.on_device(features.device):
             _C.check(_C.lib().l3d_pn2_gather_points(B, C, N, npoint, _C.ptr(features), _C.ptr(idx),
                                                     _C.ptr(output), _C.stream()), "gather_operation")
         ctx.for_backwards = (idx, C, N)
@@ -72,7 +72,7 @@ class GatherOperation(Function):
         B, npoint = idx.size()
         grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
         grad_out_data = grad_out.contiguous()
-        with torch.cuda.device(grad_out.device):
+        with _C.on_device(grad_out.device):
             _C.check(_C.lib().l3d_pn2_gather_points_grad(B, C, N, npoint, _C.ptr(grad_out_data),
                                                          _C.ptr(idx), _C.ptr(grad_features),
                                                          _C.stream()), "gather_operation backward")
@@ -94,7 +94,7 @@ class KNN(Function):
         m = known.size(1)
         dist2 = torch.empty((B, N, k), dtype=torch.float32, device=unknown.device)
         idx = torch.empty((B, N, k), dtype=torch.int32, device=unknown.device)
-        with torch.cuda.device(unknown.device):
+        with _C.on_device(unknown.device):
             _C.check(_C.lib().l3d_pn2_knn(B, N, m, k, _C.ptr(unknown), _C.ptr(known), _C.ptr(dist2),
                                           _C.ptr(idx), _C.stream()), "knn")
         ctx.mark_non_differentiable(idx)
@@ -119,7 +119,7 @@ class ThreeNN(Function):
         m = known.size(1)
         dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
         idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-        with torch.cuda.device(unknown.device):
+        with _C.on_device(unknown.device):
             _C.check(_C.lib().l3d_pn2_three_nn(B, N, m, _C.ptr(unknown), _C.ptr(known), _C.ptr(dist2),
                                                _C.ptr(idx), _C.stream()), "three_nn")
         ctx.mark_non_differentiable(idx)
@@ -146,7 +146,7 @@ class ThreeInterpolate(Function):
         n = idx.size(1)
         ctx.three_interpolate_for_backward = (idx, weight, m)
         output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _C.on_device(features.device):
             _C.check(_C.lib().l3d_pn2_three_interpolate(B, c, m, n, _C.ptr(features), _C.ptr(idx),
                                                         _C.ptr(weight), _C.ptr(output), _C.stream()),
                      "three_interpolate")
@@ -158,7 +158,7 @@ class ThreeInterpolate(Function):
         B, c, n = grad_out.size()
         grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
         grad_out_data = grad_out.contiguous()
-        with torch.cuda.device(grad_out.device):
+        with _C.on_device(grad_out.device):
             _C.check(_C.lib().l3d_pn2_three_interpolate_grad(B, c, n, m, _C.ptr(grad_out_data),
                                                              _C.ptr(idx), _C.ptr(weight),
                                                              _C.ptr(grad_features), _C.stream()),
@@ -181,7 +181,7 @@ class GroupingOperation(Function):
         B, nfeatures, nsample = idx.size()
         _, C, N = features.size()
         output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-        with torch.cuda.device(features.device):
+        with _C.on_device(features.device):
             _C.check(_C.lib().l3d_pn2_group_points(B, C, N, nfeatures, nsample, _C.ptr(features),
                                                    _C.ptr(idx), _C.ptr(output), _C.stream()),
                      "grouping_operation")
@@ -194,7 +194,7 @@ class GroupingOperation(Function):
         B, C, npoint, nsample = grad_out.size()
         grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
         grad_out_data = grad_out.contiguous()
-        with torch.cuda.device(grad_out.device):
+        with _C.on_device(grad_out.device):
             _C.check(_C.lib().l3d_pn2_group_points_grad(B, C, N, npoint, nsample, _C.ptr(grad_out_data),
                                                         _C.ptr(idx), _C.ptr(grad_features),
                                                         _C.stream()), "grouping_operation backward")
@@ -215,7 +215,7 @@ class BallQuery(Function):
         B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
         idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
+        with _C.on_device(xyz.device):
             _C.check(_C.lib().l3d_pn2_ball_query(B, N, npoint, float(radius), nsample, _C.ptr(new_xyz),
                                                  _C.ptr(xyz), _C.ptr(idx), _C.stream()), "ball_query")
         ctx.mark_non_differentiable(idx)

@@ -28,7 +28,7 @@ def knn(x, k, add_one_to_k=False):
         # same failure class as torch.topk in the reference
         raise RuntimeError("selected index k out of range")
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    with _C.on_device(x.device):
         _C.check(_C.lib().l3d_knn_expansion(_C.ptr(x), B, N, k, _C.ptr(idx), _C.ptr(None),
                                             _C.stream()), "knn")
     return idx
@@ -42,7 +42,7 @@ class _GraphFeature(torch.autograd.Function):
         B, C, N = x.shape
         k = idx.shape[-1]
         out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _C.on_device(x.device):
             _C.check(_C.lib().l3d_graph_feature(_C.ptr(x), _C.ptr(idx), B, C, N, k, _C.ptr(out),
                                                 _C.stream()), "get_graph_feature")
         ctx.save_for_backward(idx)
@@ -55,7 +55,7 @@ class _GraphFeature(torch.autograd.Function):
         B, C, N, k = ctx.dims
         grad_out = grad_out.contiguous()
         gx = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _C.on_device(grad_out.device):
             _C.check(_C.lib().l3d_graph_feature_grad(_C.ptr(grad_out), _C.ptr(idx), B, C, N, k,
                                                      _C.ptr(gx), _C.stream()),
                      "get_graph_feature backward")
@@ -87,7 +87,7 @@ def knn_point(k, pos1, pos2):
         raise RuntimeError("selected index k out of range")
     val = torch.empty((B, M, k), dtype=torch.float32, device=pos1.device)
     idx = torch.empty((B, M, k), dtype=torch.int64, device=pos1.device)
-    with torch.cuda.device(pos1.device):
+    with _C.on_device(pos1.device):
         _C.check(_C.lib().l3d_knn_point(_C.ptr(pos1), _C.ptr(pos2), B, N, M, k, _C.ptr(val),
                                         _C.ptr(idx), _C.stream()), "knn_point")
     return val, idx

@@ -19,7 +19,7 @@ class _SVDTail(torch.autograd.Function):
         B, _, N = src.shape
         R = torch.empty((B, 3, 3), dtype=torch.float32, device=src.device)
         t = torch.empty((B, 3), dtype=torch.float32, device=src.device)
-        with torch.cuda.device(src.device):
+        with _C.on_device(src.device):
             _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(src), _C.ptr(src_corr), B, N, _C.ptr(R),
                                                 _C.ptr(t), _C.stream()), "SVDHead")
         ctx.mark_non_differentiable(R, t)
