@@ -51,7 +51,16 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
   return s;  // valid on thread 0
 }
 
-// grid = (query tiles, 2 directions, B)
+// d = x2*x2 + y2*y2 + z2*z2 with x2 = candidate - query, every operation rounded (.cpp:74-77)
+__device__ __forceinline__ float chamfer_d2(const float4 cc, float qx, float qy, float qz) {
+  const float dx = __fsub_rn(cc.x, qx), dy = __fsub_rn(cc.y, qy), dz = __fsub_rn(cc.z, qz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// grid = (query tiles, 2 directions, B).  A group of CH_LPQ lanes scans the candidates for Q queries at
+// once: every candidate float4 is loaded from shared memory once per Q queries and the Q distance
+// chains are independent (ILP) — Q = 4 for large batches, 1 when the grid would otherwise be too small.
+template <int Q>
 __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFwdParams p) {
   __shared__ float4 cand[CH_CHUNK];
   __shared__ float red[CH_THREADS / 32];
@@ -63,18 +72,22 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFw
   const float* c_xyz = p.xyz[1 - dir] + (size_t)b * nc * 3;
   const int tid = threadIdx.x;
   const int grp = tid / CH_LPQ, sub = tid % CH_LPQ;
-  const int tile0 = blockIdx.x * p.passes * CH_QPP;
+  const int tile0 = blockIdx.x * p.passes * CH_QPP * Q;
   const int nchunks = (nc + CH_CHUNK - 1) / CH_CHUNK;
 
   float sqrt_sum = 0.f;
   if (tile0 < nq) {
     for (int pass = 0; pass < p.passes; ++pass) {
-      const int qi = tile0 + pass * CH_QPP + grp;
-      const bool active = qi < nq;
-      float qx = 0.f, qy = 0.f, qz = 0.f;
-      if (active) { qx = q_xyz[qi * 3]; qy = q_xyz[qi * 3 + 1]; qz = q_xyz[qi * 3 + 2]; }
-      float best = INFINITY;
-      int besti = 0;
+      int qi[Q];
+      float qx[Q], qy[Q], qz[Q], best[Q];
+      int besti[Q];
+#pragma unroll
+      for (int u = 0; u < Q; ++u) {
+        qi[u] = tile0 + (pass * Q + u) * CH_QPP + grp;
+        const int qc = min(qi[u], nq - 1);      // out-of-range slots recompute a valid query, never stored
+        qx[u] = q_xyz[qc * 3]; qy[u] = q_xyz[qc * 3 + 1]; qz[u] = q_xyz[qc * 3 + 2];
+        best[u] = INFINITY; besti[u] = 0;
+      }
       bool have = false;
       for (int c = 0; c < nchunks; ++c) {
         const int c0 = c * CH_CHUNK;
@@ -87,39 +100,41 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFw
           }
           __syncthreads();
         }
-        if (active) {
-          int j = sub;
-          if (!have && j < cn) {   // `k == 0 ||` of the reference: the first candidate is taken as is
-            const float4 cc = cand[j];
-            const float dx = __fsub_rn(cc.x, qx), dy = __fsub_rn(cc.y, qy), dz = __fsub_rn(cc.z, qz);
-            best = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            besti = c0 + j;
-            have = true;
-            j += CH_LPQ;
-          }
-#pragma unroll 8
-          for (; j < cn; j += CH_LPQ) {
-            const float4 cc = cand[j];
-            // const float x2 = xyz2[..] - x1 ...; d = x2*x2 + y2*y2 + z2*z2   (.cpp:74-77)
-            const float dx = __fsub_rn(cc.x, qx), dy = __fsub_rn(cc.y, qy), dz = __fsub_rn(cc.z, qz);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (d < best) { best = d; besti = c0 + j; }   // strict '<' (.cpp:78)
+        int j = sub;
+        if (!have && j < cn) {   // `k == 0 ||` of the reference: the first candidate is taken as is
+          const float4 cc = cand[j];
+#pragma unroll
+          for (int u = 0; u < Q; ++u) { best[u] = chamfer_d2(cc, qx[u], qy[u], qz[u]); besti[u] = c0 + j; }
+          have = true;
+          j += CH_LPQ;
+        }
+#pragma unroll 4
+        for (; j < cn; j += CH_LPQ) {
+          const float4 cc = cand[j];
+#pragma unroll
+          for (int u = 0; u < Q; ++u) {
+            const float d = chamfer_d2(cc, qx[u], qy[u], qz[u]);
+            if (d < best[u]) { best[u] = d; besti[u] = c0 + j; }   // strict '<' (.cpp:78)
           }
         }
       }
       // combine the 8 lanes of the group: smaller d, then lower index
 #pragma unroll
-      for (int o = CH_LPQ / 2; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(L3D_FULL_MASK, best, o);
-        const int oi = __shfl_xor_sync(L3D_FULL_MASK, besti, o);
-        const bool oh = __shfl_xor_sync(L3D_FULL_MASK, (int)have, o) != 0;
-        const bool take = oh && (!have || od < best || (od == best && oi < besti));
-        if (take) { best = od; besti = oi; have = true; }
-      }
-      if (active && sub == 0) {
-        p.dist[dir][(size_t)b * nq + qi] = best;
-        p.idx[dir][(size_t)b * nq + qi] = besti;
-        sqrt_sum += sqrtf(best);
+      for (int u = 0; u < Q; ++u) {
+        bool hv = have;   // a sub-lane beyond the cloud (nc < 8) holds nothing until it takes a partner's
+#pragma unroll
+        for (int o = CH_LPQ / 2; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(L3D_FULL_MASK, best[u], o);
+          const int oi = __shfl_xor_sync(L3D_FULL_MASK, besti[u], o);
+          const bool oh = __shfl_xor_sync(L3D_FULL_MASK, (int)hv, o) != 0;
+          const bool take = oh && (!hv || od < best[u] || (od == best[u] && oi < besti[u]));
+          if (take) { best[u] = od; besti[u] = oi; hv = true; }
+        }
+        if (qi[u] < nq && sub == 0) {
+          p.dist[dir][(size_t)b * nq + qi[u]] = best[u];
+          p.idx[dir][(size_t)b * nq + qi[u]] = besti[u];
+          sqrt_sum += sqrtf(best[u]);
+        }
       }
     }
   }
@@ -184,81 +199,11 @@ __device__ __forceinline__ float chamfer_g(const ChamferBwdParams& p, int side, 
   return gd * 2.0f;
 }
 
-// grid = (tiles of 256 output points, 2 sides, B).  One lane per output point; the warp scans the
-// OTHER cloud's argmin array in 32-wide coalesced chunks and hands each hit to the lane that owns
-// the target point, in ascending j — the reference's sequential accumulation order.
-__global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel(const ChamferBwdParams p) {
-  const int side = blockIdx.y, b = blockIdx.z;
-  const int other = 1 - side;
-  const int no = p.cnt[side], nx = p.cnt[other];
-  const int lane = threadIdx.x & 31;
-  const int i0 = (blockIdx.x * (CH_THREADS / 32) + (threadIdx.x >> 5)) * 32;  // warp's first point
-  if (i0 >= no) return;
-  const int i = i0 + lane;
-  const bool active = i < no;
-  const float* my = p.xyz[side] + (size_t)b * no * 3;
-  const float* ot = p.xyz[other] + (size_t)b * nx * 3;
-  const int* oidx = p.idx[other] + (size_t)b * nx;
-  const float gl_half = p.grad_loss ? (*p.grad_loss) * 0.5f : 0.f;
-
-  float px = 0.f, py = 0.f, pz = 0.f;
-  if (active) { px = my[i * 3]; py = my[i * 3 + 1]; pz = my[i * 3 + 2]; }
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  // the scan below is a chain of dependent loads: issue 8 independent 32-wide index loads at a
-  // time so their L2 latency overlaps (the kernel is latency-, not bandwidth-bound)
-  constexpr int PF = 8;
-
-  // own term: grad[i] += g*(p_i - q_idx[i])        (.cpp:153-155 / :170-172)
-  float ox = 0.f, oy = 0.f, oz = 0.f;
-  if (active) {
-    const int j2 = p.idx[side][(size_t)b * no + i];
-    const float g = chamfer_g(p, side, (size_t)b * no + i, gl_half);
-    ox = __fmul_rn(g, __fsub_rn(px, ot[j2 * 3]));
-    oy = __fmul_rn(g, __fsub_rn(py, ot[j2 * 3 + 1]));
-    oz = __fmul_rn(g, __fsub_rn(pz, ot[j2 * 3 + 2]));
-  }
-  // side 0 (xyz1): its own loop runs first, the scattered terms of loop 2 follow.
-  // side 1 (xyz2): the scattered terms of loop 1 come first, then its own loop.
-  if (side == 0) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
-
-  for (int jb = 0; jb < nx; jb += 32 * PF) {
-    int relv[PF];
-#pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int j = jb + u * 32 + lane;
-      relv[u] = (j < nx) ? (__ldg(oidx + j) - i0) : -1;
-    }
-#pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int j0 = jb + u * 32;
-      const int rel = relv[u];
-      unsigned hits = __ballot_sync(L3D_FULL_MASK, rel >= 0 && rel < 32);
-      while (hits) {
-        const int src = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int tgt = __shfl_sync(L3D_FULL_MASK, rel, src);
-        if (lane == tgt) {
-          // grad[idx[j]] -= g_j * (q_j - p_idx[j])      (.cpp:156-158 / :173-175)
-          const int jj = j0 + src;
-          const float g = chamfer_g(p, other, (size_t)b * nx + jj, gl_half);
-          ax = __fsub_rn(ax, __fmul_rn(g, __fsub_rn(ot[jj * 3], px)));
-          ay = __fsub_rn(ay, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 1], py)));
-          az = __fsub_rn(az, __fmul_rn(g, __fsub_rn(ot[jj * 3 + 2], pz)));
-        }
-      }
-    }
-  }
-  if (side == 1) { ax = __fadd_rn(ax, ox); ay = __fadd_rn(ay, oy); az = __fadd_rn(az, oz); }
-
-  if (active) {
-    float* o = p.grad[side] + ((size_t)b * no + i) * 3;
-    o[0] = ax; o[1] = ay; o[2] = az;
-  }
-}
-
-// Version 2 of the gather backward: the OTHER cloud's (x, y, z, g_j) and arg-min indices are staged
-// in shared memory per CTA, so handing a hit to its owner lane costs two LDS instead of a chain of
-// dependent global loads (v1 spent ~600 cycles per hit: 20 us at B=4 for 3 us of work).
+// grid = (tiles of 256 output points, 2 sides, B).  One lane per output point; a warp ballots 32
+// arg-min indices of the OTHER cloud at a time and hands each hit to the lane that owns the target point,
+// in ascending j — the reference's sequential accumulation order.  The other cloud's (x, y, z, g_j) and
+// arg-min indices are staged in shared memory per CTA, so a hit costs two LDS (a first version chased
+// dependent global loads: ~600 cycles per hit, 20 us at B=4 for 3 us of work).
 constexpr int CHB_CHUNK = 2048;
 __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel2(const ChamferBwdParams p) {
   __shared__ float4 s_pt[CHB_CHUNK];
@@ -330,14 +275,20 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_bwd_kernel2(const ChamferB
 
 static int chamfer_fwd_launch(ChamferFwdParams p, cudaStream_t stream, unsigned* grid_x_out) {
   const int nmax = p.cnt[0] > p.cnt[1] ? p.cnt[0] : p.cnt[1];
-  // tile size: as large as possible (amortises staging) while the grid still covers ~2 waves
-  int passes = 8;
-  while (passes > 1 && (long)((nmax + passes * CH_QPP - 1) / (passes * CH_QPP)) * 2 * p.B < 2 * 148)
-    passes >>= 1;
+  // queries per CTA = passes * Q * 32: as many as possible (Q-fold register blocking, staging amortised
+  // over `passes`) while the grid still covers ~2 waves of the 148 SMs
+  auto ctas = [&](int per_cta) { return (long)((nmax + per_cta - 1) / per_cta) * 2 * p.B; };
+  int Q = 4;
+  while (Q > 1 && ctas(Q * CH_QPP) < 2 * 148) Q >>= 1;
+  int passes = 4;
+  while (passes > 1 && ctas(passes * Q * CH_QPP) < 2 * 148) passes >>= 1;
   p.passes = passes;
-  dim3 grid((nmax + passes * CH_QPP - 1) / (passes * CH_QPP), 2, p.B);
+  const int per_cta = passes * Q * CH_QPP;
+  dim3 grid((nmax + per_cta - 1) / per_cta, 2, p.B);
   if (grid_x_out) *grid_x_out = grid.x;
-  chamfer_fwd_kernel<<<grid, CH_THREADS, 0, stream>>>(p);
+  if (Q == 4) chamfer_fwd_kernel<4><<<grid, CH_THREADS, 0, stream>>>(p);
+  else if (Q == 2) chamfer_fwd_kernel<2><<<grid, CH_THREADS, 0, stream>>>(p);
+  else chamfer_fwd_kernel<1><<<grid, CH_THREADS, 0, stream>>>(p);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
