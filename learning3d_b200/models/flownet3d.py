@@ -10,6 +10,27 @@ import torch.nn.functional as F
 from ..utils.lib import pointnet2_utils as pointutils
 
 
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """models/flownet3d.py:24-51 (torch-semantics helper kept for API parity; unused by the network)."""
+    from ..utils import farthest_point_sample, index_points, query_ball_point
+    B, N, C = xyz.shape
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz, get_cnt=False)
+    grouped_xyz = index_points(xyz, idx)
+    rel = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    new_points = rel if points is None else torch.cat([rel, index_points(points, idx)], dim=-1)
+    return (new_xyz, new_points, grouped_xyz, fps_idx) if returnfps else (new_xyz, new_points)
+
+
+def sample_and_group_all(xyz, points):
+    """models/flownet3d.py:53-70."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+    grouped = xyz.view(B, 1, N, C)
+    return new_xyz, (grouped if points is None else torch.cat([grouped, points.view(B, 1, N, -1)], dim=-1))
+
+
 def _mlp2d(channels):
     convs, bns = nn.ModuleList(), nn.ModuleList()
     for c_in, c_out in zip(channels[:-1], channels[1:]):
