@@ -1,48 +1,40 @@
-"""Drop-in for learning3d/losses/cuda/chamfer_distance/chamfer_distance.py:14-66.
-
-Same class names and tensor contract (squared distances out, int32 arg-mins saved for backward,
-gradients for both clouds).  Instead of JIT-compiling `cd` (chamfer_distance.py:11) the calls go
-to libl3d_b200.so: l3d_chamfer_forward / l3d_chamfer_backward (include/l3d_b200.h).
+"""ChamferDistanceFunction / ChamferDistance with the contract of
+learning3d/losses/cuda/chamfer_distance/chamfer_distance.py:14-66: squared nearest-neighbour distances in
+both directions, int32 arg-mins kept for backward, gradients for both clouds.  The reference JIT-compiles
+a `cd` extension at import (:11) and branches on CPU/CUDA; here both calls are entry points of
+libl3d_b200.so (l3d_chamfer_forward / l3d_chamfer_backward) and CPU tensors are an error.
 """
 import torch
 
 from .... import _C
 
 
+def _launch(symbol, anchor, *args):
+    with _C.on_device(anchor.device):
+        _C.check(getattr(_C.lib(), symbol)(*args, _C.stream()), symbol)
+
+
 class ChamferDistanceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        xyz1 = _C.require_cuda(xyz1, "xyz1")
-        xyz2 = _C.require_cuda(xyz2, "xyz2")
-        batchsize, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        dev = xyz1.device
-        dist1 = torch.empty(batchsize, n, device=dev)
-        dist2 = torch.empty(batchsize, m, device=dev)
-        idx1 = torch.empty(batchsize, n, dtype=torch.int, device=dev)
-        idx2 = torch.empty(batchsize, m, dtype=torch.int, device=dev)
-        with _C.on_device(dev):
-            _C.check(_C.lib().l3d_chamfer_forward(_C.ptr(xyz1), _C.ptr(xyz2), batchsize, n, m,
-                                                  _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1),
-                                                  _C.ptr(idx2), _C.stream()), "chamfer forward")
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        return dist1, dist2
+        p, q = _C.require_cuda(xyz1, "xyz1"), _C.require_cuda(xyz2, "xyz2")
+        B, n, m = p.size(0), p.size(1), q.size(1)
+        d_pq, d_qp = p.new_empty((B, n)), p.new_empty((B, m))
+        arg_pq = torch.empty((B, n), dtype=torch.int32, device=p.device)
+        arg_qp = torch.empty((B, m), dtype=torch.int32, device=p.device)
+        _launch("l3d_chamfer_forward", p, _C.ptr(p), _C.ptr(q), B, n, m, _C.ptr(d_pq), _C.ptr(d_qp),
+                _C.ptr(arg_pq), _C.ptr(arg_qp))
+        ctx.save_for_backward(p, q, arg_pq, arg_qp)
+        return d_pq, d_qp
 
     @staticmethod
     def backward(ctx, graddist1, graddist2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        graddist1 = graddist1.contiguous()
-        graddist2 = graddist2.contiguous()
-        batchsize, n, _ = xyz1.size()
-        m = xyz2.size(1)
-        gradxyz1 = torch.empty_like(xyz1)
-        gradxyz2 = torch.empty_like(xyz2)
-        with _C.on_device(xyz1.device):
-            _C.check(_C.lib().l3d_chamfer_backward(
-                _C.ptr(xyz1), _C.ptr(xyz2), batchsize, n, m, _C.ptr(graddist1), _C.ptr(graddist2),
-                _C.ptr(idx1), _C.ptr(idx2), _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.stream()),
-                "chamfer backward")
-        return gradxyz1, gradxyz2
+        p, q, arg_pq, arg_qp = ctx.saved_tensors
+        g1, g2 = graddist1.contiguous(), graddist2.contiguous()
+        grad_p, grad_q = torch.empty_like(p), torch.empty_like(q)     # fully overwritten: no memset
+        _launch("l3d_chamfer_backward", p, _C.ptr(p), _C.ptr(q), p.size(0), p.size(1), q.size(1), _C.ptr(g1),
+                _C.ptr(g2), _C.ptr(arg_pq), _C.ptr(arg_qp), _C.ptr(grad_p), _C.ptr(grad_q))
+        return grad_p, grad_q
 
 
 class ChamferDistance(torch.nn.Module):

@@ -39,6 +39,15 @@ def _mlp2d(channels):
     return convs, bns
 
 
+def _knn_groups(nsample, pos1, pos2, feature2):
+    """For every point of pos1 [B,3,N]: its nsample nearest points of pos2 [B,3,M] as centre-relative offsets
+    [B,3,N,S] and their gathered features [B,C,N,S] (reference call sites :157-167 and :222-229)."""
+    B, _, N = pos1.shape
+    _, idx = pointutils.knn(nsample, pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
+    offsets = pointutils.grouping_operation(pos2.contiguous(), idx) - pos1.view(B, -1, N, 1)
+    return offsets, pointutils.grouping_operation(feature2.contiguous(), idx)
+
+
 class PointNetSetAbstraction(nn.Module):
     def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
         super().__init__()
@@ -70,11 +79,9 @@ class FlowEmbedding(nn.Module):
 
     def forward(self, pos1, pos2, feature1, feature2):
         B, _, N = pos1.shape
-        _, idx = pointutils.knn(self.nsample, pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
-        pos_diff = pointutils.grouping_operation(pos2.contiguous(), idx) - pos1.view(B, -1, N, 1)
-        feat2_grouped = pointutils.grouping_operation(feature2.contiguous(), idx)
-        feat = torch.cat([pos_diff, feat2_grouped,
-                          feature1.view(B, -1, N, 1).repeat(1, 1, 1, self.nsample)], dim=1)
+        offsets, neighbours = _knn_groups(self.nsample, pos1, pos2, feature2)
+        own = feature1.view(B, -1, N, 1).expand(-1, -1, -1, self.nsample)
+        feat = torch.cat([offsets, neighbours, own], dim=1)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             feat = F.relu(bn(conv(feat)))
         return pos1, torch.max(feat, -1)[0]
@@ -99,10 +106,8 @@ class PointNetSetUpConv(nn.Module):
             last = c_out
 
     def forward(self, pos1, pos2, feature1, feature2):
-        B, _, N = pos1.shape
-        _, idx = pointutils.knn(self.nsample, pos1.permute(0, 2, 1).contiguous(), pos2.permute(0, 2, 1).contiguous())
-        pos_diff = pointutils.grouping_operation(pos2.contiguous(), idx) - pos1.view(B, -1, N, 1)
-        feat = torch.cat([pointutils.grouping_operation(feature2.contiguous(), idx), pos_diff], dim=1)
+        offsets, neighbours = _knn_groups(self.nsample, pos1, pos2, feature2)
+        feat = torch.cat([neighbours, offsets], dim=1)
         for conv in self.mlp1_convs:
             feat = conv(feat)
         feat = feat.max(-1)[0]
@@ -155,17 +160,19 @@ class FlowNet3D(nn.Module):
         self.bn1 = nn.BatchNorm1d(128)
         self.conv2 = nn.Conv1d(128, 3, kernel_size=1, bias=True)
 
+    def _encode(self, pc, feat):
+        """Two set-abstraction levels: (xyz, features) at 1024 and at 256 points."""
+        lvl1 = self.sa1(pc, feat)
+        return lvl1, self.sa2(*lvl1)
+
     def forward(self, pc1, pc2, feature1, feature2):
-        l1_pc1, l1_f1 = self.sa1(pc1, feature1)
-        l2_pc1, l2_f1 = self.sa2(l1_pc1, l1_f1)
-        l1_pc2, l1_f2 = self.sa1(pc2, feature2)
-        l2_pc2, l2_f2 = self.sa2(l1_pc2, l1_f2)
-        _, l2_f1_new = self.fe_layer(l2_pc1, l2_pc2, l2_f1, l2_f2)
-        l3_pc1, l3_f1 = self.sa3(l2_pc1, l2_f1_new)
-        l4_pc1, l4_f1 = self.sa4(l3_pc1, l3_f1)
-        l3_fnew1 = self.su1(l3_pc1, l4_pc1, l3_f1, l4_f1)
-        l2_fnew1 = self.su2(l2_pc1, l3_pc1, torch.cat([l2_f1, l2_f1_new], dim=1), l3_fnew1)
-        l1_fnew1 = self.su3(l1_pc1, l2_pc1, l1_f1, l2_fnew1)
-        l0_fnew1 = self.fp(pc1, l1_pc1, feature1, l1_fnew1)
-        x = F.relu(self.bn1(self.conv1(l0_fnew1)))
-        return self.conv2(x)
+        (p1, f1), (p2, f2) = self._encode(pc1, feature1)            # frame 1 pyramid
+        _, (q2, g2) = self._encode(pc2, feature2)                    # frame 2, coarse level only
+        _, mixed = self.fe_layer(p2, q2, f2, g2)                     # flow embedding at 256 points
+        p3, f3 = self.sa3(p2, mixed)
+        p4, f4 = self.sa4(p3, f3)
+        up3 = self.su1(p3, p4, f3, f4)                               # decoder: 16 -> 64 -> 256 -> 1024
+        up2 = self.su2(p2, p3, torch.cat([f2, mixed], dim=1), up3)
+        up1 = self.su3(p1, p2, f1, up2)
+        dense = self.fp(pc1, p1, feature1, up1)                      # back to the input resolution
+        return self.conv2(F.relu(self.bn1(self.conv1(dense))))

@@ -105,6 +105,16 @@ def knn_sqdist(nsample, xyz, new_xyz):
     return idx
 
 
+def group_around(xyz, centres, idx, feats=None):
+    """Gather the neighbourhoods `idx` [B,S,K] of `xyz` [B,N,C], express them relative to their centres
+    [B,S,C] and optionally append gathered per-point features.  Returns (absolute, relative, merged) —
+    the tail shared by every sample_and_group / group composition of the reference."""
+    absolute = index_points(xyz, idx)
+    relative = absolute - centres.unsqueeze(2)
+    merged = relative if feats is None else torch.cat([relative, index_points(feats, idx)], dim=-1)
+    return absolute, relative, merged
+
+
 def compute_density(xyz, bandwidth):
     """pointconv_util.py:199-209 — fused row reduction, the N x N matrix is never materialised."""
     xyz = _xyz(xyz, "xyz")

@@ -1,223 +1,173 @@
-"""Drop-in for learning3d/utils/lib/pointnet2_utils.py:10-318.
-
-Same public names (furthest_point_sample, gather_operation, knn, three_nn, three_interpolate,
-grouping_operation, ball_query, QueryAndGroup, GroupAll) and tensor contracts (int32 indices,
-[B,C,N] feature layout, gradients only through gather / group / interpolate).  The reference binds
-`pointnet2_cuda` (utils/lib/src/pointnet2_api.cpp:10-25), which no longer builds (THC removed);
-here every call goes to libl3d_b200.so (include/l3d_b200.h, "pointnet2_cuda replacements").
+"""pointnet2 ops on libl3d_b200.so — the public surface of learning3d/utils/lib/pointnet2_utils.py
+(:10-318): furthest_point_sample, gather_operation, knn, three_nn, three_interpolate,
+grouping_operation, ball_query, QueryAndGroup, GroupAll; int32 indices, [B,C,N] features, gradients only
+through gather / group / interpolate.  The reference binds the `pointnet2_cuda` extension
+(utils/lib/src/pointnet2_api.cpp:10-25), which needs THC and no longer builds; here each op is one call
+into the C ABI (include/l3d_b200.h, "pointnet2_cuda replacements") on the caller's current stream.
 """
-from typing import Tuple
-
 import torch
 import torch.nn as nn
 from torch.autograd import Function
 
 from ... import _C
 
-
-def _f32(t, name):
-    return _C.require_cuda(t, name)
+_F32, _I32 = torch.float32, torch.int32
 
 
-def _i32(t, name):
+def _run(symbol, anchor, *args):
+    """Launch `symbol` on anchor's device / current stream; raise on a non-zero return code."""
+    with _C.on_device(anchor.device):
+        _C.check(getattr(_C.lib(), symbol)(*args, _C.stream()), symbol)
+
+
+def _feat(t, what):
+    if not t.is_contiguous():
+        raise AssertionError("%s must be contiguous" % what)     # the reference asserts contiguity
+    return _C.require_cuda(t, what)
+
+
+def _index(t, what):
     if not t.is_cuda:
-        raise RuntimeError("learning3d_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
-    return t.to(torch.int32).contiguous()
+        raise RuntimeError("learning3d_b200: %s must be a CUDA tensor (no CPU fallback)" % what)
+    if not t.is_contiguous():
+        raise AssertionError("%s must be contiguous" % what)
+    return t if t.dtype == _I32 else t.to(_I32)
 
 
 class FurthestPointSampling(Function):
-    @staticmethod
-    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
-        """xyz (B, N, 3) -> (B, npoint) int32, first index 0   (pointnet2_utils.py:12-29)."""
-        assert xyz.is_contiguous()
-        xyz = _f32(xyz, "xyz")
-        B, N, _ = xyz.size()
-        output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-        with _C.on_device(xyz.device):
-            _C.check(_C.lib().l3d_pn2_furthest_point_sampling(B, N, npoint, _C.ptr(xyz), _C.ptr(temp),
-                                                              _C.ptr(output), _C.stream()),
-                     "furthest_point_sample")
-        ctx.mark_non_differentiable(output)
-        return output
+    """(B, N, 3) cloud -> (B, npoint) int32 sample indices, index 0 first (pointnet2_utils.py:10-36)."""
 
     @staticmethod
-    def backward(ctx, a=None):
+    def forward(ctx, xyz, npoint):
+        xyz = _feat(xyz, "xyz")
+        B, N = xyz.shape[0], xyz.shape[1]
+        picked = torch.empty((B, npoint), dtype=_I32, device=xyz.device)
+        running_min = torch.full((B, N), 1e10, dtype=_F32, device=xyz.device)
+        _run("l3d_pn2_furthest_point_sampling", xyz, B, N, npoint, _C.ptr(xyz), _C.ptr(running_min), _C.ptr(picked))
+        ctx.mark_non_differentiable(picked)
+        return picked
+
+    @staticmethod
+    def backward(ctx, grad=None):
         return None, None
 
 
-furthest_point_sample = FurthestPointSampling.apply
-
-
 class GatherOperation(Function):
+    """features (B, C, N), idx (B, npoint) -> (B, C, npoint) (pointnet2_utils.py:38-70)."""
+
     @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        """features (B, C, N), idx (B, npoint) -> (B, C, npoint)   (pointnet2_utils.py:40-60)."""
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        features = _f32(features, "features")
-        idx = _i32(idx, "idx")
-        B, npoint = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-        with _C.on_device(features.device):
-            _C.check(_C.lib().l3d_pn2_gather_points(B, C, N, npoint, _C.ptr(features), _C.ptr(idx),
-                                                    _C.ptr(output), _C.stream()), "gather_operation")
+    def forward(ctx, features, idx):
+        features, idx = _feat(features, "features"), _index(idx, "idx")
+        (B, C, N), npoint = features.shape, idx.shape[1]
+        out = torch.empty((B, C, npoint), dtype=_F32, device=features.device)
+        _run("l3d_pn2_gather_points", features, B, C, N, npoint, _C.ptr(features), _C.ptr(idx), _C.ptr(out))
         ctx.for_backwards = (idx, C, N)
-        return output
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
         idx, C, N = ctx.for_backwards
-        B, npoint = idx.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        grad_out_data = grad_out.contiguous()
-        with _C.on_device(grad_out.device):
-            _C.check(_C.lib().l3d_pn2_gather_points_grad(B, C, N, npoint, _C.ptr(grad_out_data),
-                                                         _C.ptr(idx), _C.ptr(grad_features),
-                                                         _C.stream()), "gather_operation backward")
-        return grad_features, None
+        g = grad_out.contiguous()
+        B, npoint = idx.shape
+        acc = torch.zeros((B, C, N), dtype=_F32, device=g.device)
+        _run("l3d_pn2_gather_points_grad", g, B, C, N, npoint, _C.ptr(g), _C.ptr(idx), _C.ptr(acc))
+        return acc, None
 
 
-gather_operation = GatherOperation.apply
+def _nearest(symbol, k, unknown, known, with_k):
+    unknown, known = _feat(unknown, "unknown"), _feat(known, "known")
+    B, n, m = unknown.shape[0], unknown.shape[1], known.shape[1]
+    d2 = torch.empty((B, n, k), dtype=_F32, device=unknown.device)
+    idx = torch.empty((B, n, k), dtype=_I32, device=unknown.device)
+    dims = (B, n, m, k) if with_k else (B, n, m)
+    _run(symbol, unknown, *dims, _C.ptr(unknown), _C.ptr(known), _C.ptr(d2), _C.ptr(idx))
+    return torch.sqrt(d2), idx
 
 
 class KNN(Function):
+    """k nearest `known` (B, M, 3) points of every `unknown` (B, N, 3) query: (L2 distance, int32 index),
+    nearest first (pointnet2_utils.py:72-101)."""
+
     @staticmethod
-    def forward(ctx, k: int, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """unknown (B, N, 3) queries, known (B, M, 3) -> (sqrt(d2) (B, N, k), idx int32)
-        (pointnet2_utils.py:74-97)."""
-        assert unknown.is_contiguous()
-        assert known.is_contiguous()
-        unknown, known = _f32(unknown, "unknown"), _f32(known, "known")
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty((B, N, k), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, N, k), dtype=torch.int32, device=unknown.device)
-        with _C.on_device(unknown.device):
-            _C.check(_C.lib().l3d_pn2_knn(B, N, m, k, _C.ptr(unknown), _C.ptr(known), _C.ptr(dist2),
-                                          _C.ptr(idx), _C.stream()), "knn")
+    def forward(ctx, k, unknown, known):
+        dist, idx = _nearest("l3d_pn2_knn", k, unknown, known, True)
         ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
+        return dist, idx
 
     @staticmethod
     def backward(ctx, a=None, b=None):
         return None, None, None
 
 
-knn = KNN.apply
-
-
 class ThreeNN(Function):
+    """The k = 3 case used by feature propagation (pointnet2_utils.py:104-130)."""
+
     @staticmethod
-    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(pointnet2_utils.py:104-126)."""
-        assert unknown.is_contiguous()
-        assert known.is_contiguous()
-        unknown, known = _f32(unknown, "unknown"), _f32(known, "known")
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-        with _C.on_device(unknown.device):
-            _C.check(_C.lib().l3d_pn2_three_nn(B, N, m, _C.ptr(unknown), _C.ptr(known), _C.ptr(dist2),
-                                               _C.ptr(idx), _C.stream()), "three_nn")
+    def forward(ctx, unknown, known):
+        dist, idx = _nearest("l3d_pn2_three_nn", 3, unknown, known, False)
         ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
+        return dist, idx
 
     @staticmethod
     def backward(ctx, a=None, b=None):
         return None, None
 
 
-three_nn = ThreeNN.apply
-
-
 class ThreeInterpolate(Function):
+    """features (B, C, M), idx / weight (B, n, 3) -> weighted sum of three gathered columns (B, C, n)
+    (pointnet2_utils.py:135-185)."""
+
     @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-        """features (B, C, M), idx (B, n, 3), weight (B, n, 3) -> (B, C, n)   (pointnet2_utils.py:137-161)."""
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        assert weight.is_contiguous()
-        features, weight = _f32(features, "features"), _f32(weight, "weight")
-        idx = _i32(idx, "idx")
-        B, c, m = features.size()
-        n = idx.size(1)
+    def forward(ctx, features, idx, weight):
+        features, weight, idx = _feat(features, "features"), _feat(weight, "weight"), _index(idx, "idx")
+        (B, C, m), n = features.shape, idx.shape[1]
+        out = torch.empty((B, C, n), dtype=_F32, device=features.device)
+        _run("l3d_pn2_three_interpolate", features, B, C, m, n, _C.ptr(features), _C.ptr(idx), _C.ptr(weight), _C.ptr(out))
         ctx.three_interpolate_for_backward = (idx, weight, m)
-        output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-        with _C.on_device(features.device):
-            _C.check(_C.lib().l3d_pn2_three_interpolate(B, c, m, n, _C.ptr(features), _C.ptr(idx),
-                                                        _C.ptr(weight), _C.ptr(output), _C.stream()),
-                     "three_interpolate")
-        return output
+        return out
 
     @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
+    def backward(ctx, grad_out):
         idx, weight, m = ctx.three_interpolate_for_backward
-        B, c, n = grad_out.size()
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-        grad_out_data = grad_out.contiguous()
-        with _C.on_device(grad_out.device):
-            _C.check(_C.lib().l3d_pn2_three_interpolate_grad(B, c, n, m, _C.ptr(grad_out_data),
-                                                             _C.ptr(idx), _C.ptr(weight),
-                                                             _C.ptr(grad_features), _C.stream()),
-                     "three_interpolate backward")
-        return grad_features, None, None
-
-
-three_interpolate = ThreeInterpolate.apply
+        g = grad_out.contiguous()
+        B, C, n = g.shape
+        acc = torch.zeros((B, C, m), dtype=_F32, device=g.device)
+        _run("l3d_pn2_three_interpolate_grad", g, B, C, n, m, _C.ptr(g), _C.ptr(idx), _C.ptr(weight), _C.ptr(acc))
+        return acc, None, None
 
 
 class GroupingOperation(Function):
+    """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample) (pointnet2_utils.py:188-225)."""
+
     @staticmethod
-    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-        """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample)
-        (pointnet2_utils.py:186-205)."""
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        features = _f32(features, "features")
-        idx = _i32(idx, "idx")
-        B, nfeatures, nsample = idx.size()
-        _, C, N = features.size()
-        output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-        with _C.on_device(features.device):
-            _C.check(_C.lib().l3d_pn2_group_points(B, C, N, nfeatures, nsample, _C.ptr(features),
-                                                   _C.ptr(idx), _C.ptr(output), _C.stream()),
-                     "grouping_operation")
+    def forward(ctx, features, idx):
+        features, idx = _feat(features, "features"), _index(idx, "idx")
+        (B, C, N), (_, npoint, nsample) = features.shape, idx.shape
+        out = torch.empty((B, C, npoint, nsample), dtype=_F32, device=features.device)
+        _run("l3d_pn2_group_points", features, B, C, N, npoint, nsample, _C.ptr(features), _C.ptr(idx), _C.ptr(out))
         ctx.for_backwards = (idx, N)
-        return output
+        return out
 
     @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
+    def backward(ctx, grad_out):
         idx, N = ctx.for_backwards
-        B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        grad_out_data = grad_out.contiguous()
-        with _C.on_device(grad_out.device):
-            _C.check(_C.lib().l3d_pn2_group_points_grad(B, C, N, npoint, nsample, _C.ptr(grad_out_data),
-                                                        _C.ptr(idx), _C.ptr(grad_features),
-                                                        _C.stream()), "grouping_operation backward")
-        return grad_features, None
-
-
-grouping_operation = GroupingOperation.apply
+        g = grad_out.contiguous()
+        B, C, npoint, nsample = g.shape
+        acc = torch.zeros((B, C, N), dtype=_F32, device=g.device)
+        _run("l3d_pn2_group_points_grad", g, B, C, N, npoint, nsample, _C.ptr(g), _C.ptr(idx), _C.ptr(acc))
+        return acc, None
 
 
 class BallQuery(Function):
+    """First `nsample` indices (ascending) of xyz (B, N, 3) within `radius` of each centre new_xyz
+    (B, npoint, 3), padded with the first hit (pointnet2_utils.py:228-254)."""
+
     @staticmethod
-    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-        """xyz (B, N, 3), new_xyz (B, npoint, 3) -> idx (B, npoint, nsample) int32
-        (pointnet2_utils.py:231-248)."""
-        assert new_xyz.is_contiguous()
-        assert xyz.is_contiguous()
-        xyz, new_xyz = _f32(xyz, "xyz"), _f32(new_xyz, "new_xyz")
-        B, N, _ = xyz.size()
-        npoint = new_xyz.size(1)
-        idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-        with _C.on_device(xyz.device):
-            _C.check(_C.lib().l3d_pn2_ball_query(B, N, npoint, float(radius), nsample, _C.ptr(new_xyz),
-                                                 _C.ptr(xyz), _C.ptr(idx), _C.stream()), "ball_query")
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        new_xyz, xyz = _feat(new_xyz, "new_xyz"), _feat(xyz, "xyz")
+        B, N, npoint = xyz.shape[0], xyz.shape[1], new_xyz.shape[1]
+        idx = torch.empty((B, npoint, nsample), dtype=_I32, device=xyz.device)
+        _run("l3d_pn2_ball_query", xyz, B, N, npoint, float(radius), nsample, _C.ptr(new_xyz), _C.ptr(xyz), _C.ptr(idx))
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -226,48 +176,47 @@ class BallQuery(Function):
         return None, None, None, None
 
 
+furthest_point_sample = FurthestPointSampling.apply
+gather_operation = GatherOperation.apply
+knn = KNN.apply
+three_nn = ThreeNN.apply
+three_interpolate = ThreeInterpolate.apply
+grouping_operation = GroupingOperation.apply
 ball_query = BallQuery.apply
 
 
-class QueryAndGroup(nn.Module):
-    """pointnet2_utils.py:259-295."""
+def _stack_xyz_and_features(grouped_xyz, grouped_features, use_xyz):
+    if grouped_features is None:
+        if not use_xyz:
+            raise AssertionError("Cannot have not features and not use xyz as a feature!")
+        return grouped_xyz
+    return torch.cat([grouped_xyz, grouped_features], dim=1) if use_xyz else grouped_features
 
-    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+
+class QueryAndGroup(nn.Module):
+    """Ball query + grouping with centre-relative coordinates: (B, 3 + C, npoint, nsample)
+    (pointnet2_utils.py:257-295)."""
+
+    def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+    def forward(self, xyz, new_xyz, features=None):
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)
-            else:
-                new_features = grouped_features
-        else:
-            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz
-        return new_features
+        rel = grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
+        grouped = None if features is None else grouping_operation(features, idx)
+        return _stack_xyz_and_features(rel, grouped, self.use_xyz)
 
 
 class GroupAll(nn.Module):
-    """pointnet2_utils.py:298-318."""
+    """One group holding the whole cloud: (B, 3 + C, 1, N) (pointnet2_utils.py:298-318)."""
 
-    def __init__(self, use_xyz: bool = True):
+    def __init__(self, use_xyz=True):
         super().__init__()
         self.use_xyz = use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)
-            else:
-                new_features = grouped_features
-        else:
-            new_features = grouped_xyz
-        return new_features
+    def forward(self, xyz, new_xyz, features=None):
+        whole = xyz.transpose(1, 2).unsqueeze(2)
+        if features is None:
+            return whole
+        return _stack_xyz_and_features(whole, features.unsqueeze(2), self.use_xyz)
