@@ -99,7 +99,12 @@ def stream():
 
 
 def ptr(t):
-    return _P(t.data_ptr()) if t is not None else _P(None)
+    """Device pointer of a tensor (None -> NULL = "argument not given").  An EMPTY tensor has a null
+    data_ptr; the ABI treats NULL as a missing argument, so empty tensors pass a never-dereferenced
+    non-null sentinel and the entry point returns L3D_OK on its `B == 0` early-out."""
+    if t is None:
+        return _P(None)
+    return _P(t.data_ptr() or 16)
 
 
 def require_cuda(t, name, dtype=torch.float32):

@@ -637,9 +637,9 @@ static int knn_launch_t(KnnParams p, cudaStream_t stream) {
 template <int MODE, bool SELF, bool CAND_BCN>
 static int knn_launch(KnnParams p, cudaStream_t stream) {
   if (p.B < 0 || p.N < 1 || p.M < 0 || p.k < 1 || p.k > p.N) return L3D_ERR_INVALID;
+  if ((long)p.B * p.M == 0) return L3D_OK;   // empty batch: nothing to do (its pointers may be null)
   if (!p.cand || !p.out_idx || (!SELF && !p.query)) return L3D_ERR_INVALID;
   if (p.N > L3D_KNN_MAX_N || p.k > 128) return L3D_ERR_UNSUPPORTED;
-  if ((long)p.B * p.M == 0) return L3D_OK;
   p.force_slow = g_force_slow;
   p.use_tma = ((reinterpret_cast<uintptr_t>(p.cand) & 15u) == 0 && (p.N & 3) == 0) ? 1 : 0;
   // Heavy selections out of a small cloud (FlowNet3D's flow embedding: k = 64 of N = 256) sort the
