@@ -3,3 +3,4 @@ the dense layers (1x1 convs, BatchNorm) are plain torch as in the reference — 
 kernels — while every neighbour search / grouping call lands in libl3d_b200.so."""
 from .dgcnn import DGCNN
 from .flownet3d import FlowNet3D
+from .dcp import DCP

@@ -5,6 +5,7 @@ import at utils/__init__.py:5-14 shadows the ppfnet_util ones); the pointconv_ut
 variants stay reachable under their own module paths.
 """
 from .svd import SVDHead
+from .transformer import Transformer, Identity
 from .ppfnet_util import angle_difference, sample_and_group, sample_and_group_multi
 from .model_common_utils import (
     knn,

@@ -150,12 +150,49 @@ def gen_svd():
          src_corr=src_corr.numpy(), R=R.numpy(), t=t.numpy())
 
 
+def gen_dcp():
+    """DCP (models/dcp.py:10-55) = DGCNN + Transformer + SVDHead on CPU, eval mode, small seeded weights
+    (emb_dims 32) so the state_dict fits in a fixture; source = rigidly moved template."""
+    from learning3d.models import DCP, DGCNN
+    best = None
+    for seed in range(40):
+        torch.manual_seed(1000 + seed)
+        net = DCP(feature_model=DGCNN(emb_dims=32), cycle=True).eval()
+        template = torch.rand(2, 128, 3) - 0.5
+        ang = torch.tensor([0.5, -0.7])
+        c, s_ = torch.cos(ang), torch.sin(ang)
+        R = torch.zeros(2, 3, 3); R[:, 0, 0] = c; R[:, 0, 1] = -s_; R[:, 1, 0] = s_; R[:, 1, 1] = c; R[:, 2, 2] = 1
+        source = torch.matmul(template, R.transpose(1, 2)) + torch.tensor([[0.1, -0.2, 0.05], [0.0, 0.3, -0.1]])[:, None]
+        with torch.no_grad():
+            out = net(template, source)
+            # conditioning of the 3x3 the head decomposes: recompute H as svd.py:23-33 does
+            sf, tf = net.emb_nn(source), net.emb_nn(template)
+            sp, tp = net.pointer(sf, tf)
+            sf, tf = sf + sp, tf + tp
+            scores = torch.softmax(torch.matmul(sf.transpose(2, 1).contiguous(), tf) / 32 ** 0.5, dim=2)
+            corr = torch.matmul(template.permute(0, 2, 1), scores.transpose(2, 1).contiguous())
+            srcT = source.permute(0, 2, 1)
+            H = torch.matmul(srcT - srcT.mean(2, keepdim=True), (corr - corr.mean(2, keepdim=True)).transpose(2, 1))
+            sv = torch.linalg.svdvals(H)
+            cond = (sv[:, 2] / sv[:, 0]).min().item()
+        if best is None or cond > best[0]:
+            best = (cond, seed, net, template, source, out)
+    cond, seed, net, template, source, out = best
+    print("dcp fixture: seed", seed, "sigma_min/sigma_max", cond)
+    arrays = {"template": template.numpy(), "source": source.numpy()}
+    for k in ("est_R", "est_t", "est_R_", "est_t_", "est_T", "transformed_source"):
+        arrays["out_" + k] = out[k].numpy()
+    for k, v in net.state_dict().items():
+        arrays["sd::" + k] = v.numpy()
+    save("dcp_small", **arrays)
+
+
 if __name__ == "__main__":
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     os.environ.setdefault("TORCH_EXTENSIONS_DIR", tempfile.mkdtemp(prefix="l3dref_ext_"))
     os.environ["CC"] = "/usr/bin/gcc"; os.environ["CXX"] = "/usr/bin/g++"
     import_reference()
-    which = sys.argv[1:] or ["knn", "chamfer", "group", "svd"]
+    which = sys.argv[1:] or ["knn", "chamfer", "group", "svd", "dcp"]
     if "knn" in which:
         gen_knn()
     if "chamfer" in which:
@@ -164,3 +201,5 @@ if __name__ == "__main__":
         gen_group()
     if "svd" in which:
         gen_svd()
+    if "dcp" in which:
+        gen_dcp()
