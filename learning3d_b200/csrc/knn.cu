@@ -39,12 +39,9 @@ constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
 #ifndef L3D_KNN_R
 #define L3D_KNN_R 2
 #endif
-#ifndef L3D_KNN_RANK_SELECT
-// 0: exchange-network selection (default), 1: rank-by-counting selection.  The counting variant removes
-// the chain of dependent shuffles but measured SLOWER (40.9 vs 36.2 us at C2, profiles/r01): its broadcast
-// LDS + 64-bit compares cost more issue slots than the latency they hide.  Kept for experiments.
-#define L3D_KNN_RANK_SELECT 0
-#endif
+// Selection variants that were measured and dropped (profiles/r01): rank-by-counting
+// against the shared-memory survivor list (40.9 us), an FMNMX key/value network with tie fallback
+// (37.2 us) — both slower than the 64-bit composite network below (36.1 us at C2).
 // Register budget: left to ptxas' own heuristic by default (127 registers at R = 2, 2 CTAs/SM), which
 // measured fastest; forcing min-blocks 1..5 (48..167 registers) was 10-35 % slower (profiles/r01).
 #ifdef L3D_KNN_MIN_BLOCKS
@@ -446,61 +443,6 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
     __syncwarp();
     // first 32 survivors of every row: one straight-line network over all R rows (the exchanges of
     // different rows are independent, so their shuffle latencies overlap)
-#if L3D_KNN_RANK_SELECT
-    // Selection by RANK COUNTING: every lane reads all survivors back from shared memory (broadcast
-    // LDS.64, independent loads) and counts how many beat its own one or two; the count is the final
-    // position.  Same instruction count as a 15..36-stage exchange network but no chain of dependent
-    // shuffles (short-scoreboard was the top stall of the network version, profiles/r01).
-    unsigned long long e0[R], e1[R];
-    int n_in[R], rk0[R], rk1[R];
-    int nmax = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      n_in[r] = ovf[r] ? 0 : base[r] + total[r];
-      e0[r] = (lane < n_in[r]) ? cbuf[r * CAP + lane] : 0ull;
-      e1[r] = (lane + 32 < n_in[r]) ? cbuf[r * CAP + lane + 32] : 0ull;
-      rk0[r] = 0; rk1[r] = 0;
-      nmax = max(nmax, n_in[r]);
-    }
-    if (nmax <= 32) {
-#pragma unroll 4
-      for (int j = 0; j < nmax; ++j) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const unsigned long long o = cbuf[r * CAP + j];
-          rk0[r] += (j < n_in[r] && o > e0[r]) ? 1 : 0;
-        }
-      }
-    } else {
-#pragma unroll 4
-      for (int j = 0; j < nmax; ++j) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const unsigned long long o = cbuf[r * CAP + j];
-          const bool live = j < n_in[r];
-          rk0[r] += (live && o > e0[r]) ? 1 : 0;
-          rk1[r] += (live && o > e1[r]) ? 1 : 0;
-        }
-      }
-    }
-    __syncwarp();
-    // put every survivor at its rank (ranks are a permutation of 0..n-1), then lane l picks up rank l
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (lane < n_in[r] && rk0[r] < 32) cbuf[r * CAP + rk0[r]] = e0[r];
-      if (lane + 32 < n_in[r] && rk1[r] < 32) cbuf[r * CAP + rk1[r]] = e1[r];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      best[r] = (lane < min(n_in[r], 32)) ? cbuf[r * CAP + lane] : 0ull;
-      if (t + 1 < ntiles) {
-        kth[r] = f32_unorder(__shfl_sync(L3D_FULL_MASK, (uint32_t)(best[r] >> 32), k - 1));
-        base[r] = k;
-      }
-    }
-    __syncwarp();
-#else
     unsigned long long a[R];
     int n_in[R];
 #pragma unroll
@@ -527,7 +469,6 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
       }
     }
     __syncwarp();
-#endif
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
