@@ -267,6 +267,12 @@ int l3d_kabsch3x3_batched(const float* H_dev, const float* src_mean_dev, const f
 /* Same, fused with the centring and the H reduction: src_dev, src_corr_dev [B,3,N] (svd.py:29-33). */
 int l3d_svd_head_tail(const float* src_dev, const float* src_corr_dev, int B, int N, float* R_dev,
                       float* t_dev, void* stream);
+/* Backward of l3d_svd_head_tail (what autograd derives through torch.svd / torch.det in the reference's
+ * training scripts, examples/train_dcp.py): grad_R_dev [B,3,3], grad_t_dev [B,3] ->
+ * grad_src_dev, grad_src_corr_dev [B,3,N].  Closed-form SVD differential, fp64 inside. */
+int l3d_svd_head_tail_backward(const float* src_dev, const float* src_corr_dev, const float* grad_R_dev,
+                               const float* grad_t_dev, int B, int N, float* grad_src_dev,
+                               float* grad_src_corr_dev, void* stream);
 
 #ifdef __cplusplus
 }

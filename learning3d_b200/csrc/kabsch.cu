@@ -14,8 +14,11 @@
 
 namespace l3d {
 
+// `fact` (optional, 22 doubles): U (9, row-major), V (9), sigma (3, descending), d = +-1 of the
+// determinant fix — what the backward pass needs.
 __device__ void kabsch_from_H(const double Hin[9], const float mu_s[3], const float mu_c[3],
-                              float* __restrict__ R_out, float* __restrict__ t_out) {
+                              float* __restrict__ R_out, float* __restrict__ t_out,
+                              double* __restrict__ fact = nullptr) {
   double A[3][3], V[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -102,11 +105,23 @@ __device__ void kabsch_from_H(const double Hin[9], const float mu_s[3], const fl
 #pragma unroll
       for (int j = 0; j < 3; ++j) R[i][j] -= 2.0 * V[i][2] * U[j][2];
   }
+  if (fact) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { fact[i * 3 + j] = U[i][j]; fact[9 + i * 3 + j] = V[i][j]; }
+    fact[18] = sig[0]; fact[19] = sig[1]; fact[20] = sig[2];
+    fact[21] = det < 0 ? -1.0 : 1.0;
+  }
   float Rf[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { Rf[i * 3 + j] = (float)R[i][j]; R_out[i * 3 + j] = Rf[i * 3 + j]; }
+    for (int j = 0; j < 3; ++j) {
+      Rf[i * 3 + j] = (float)R[i][j];
+      if (R_out) R_out[i * 3 + j] = Rf[i * 3 + j];
+    }
+  if (!t_out) return;
   // t = matmul(-R, mean(src)) + mean(src_corr)   (svd.py:58), fp32 like the reference
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -181,6 +196,129 @@ __global__ void __launch_bounds__(SVDH_THREADS) svd_head_tail_kernel(const float
   }
 }
 
+// ---- backward of the SVD-head tail ---------------------------------------------------------------
+// R = V D U^T (D = diag(1,1,d)), t = -R mu_s + mu_c, H = sum_n (s_n - mu_s)(c_n - mu_c)^T = U S V^T.
+// With G = dL/dR - g_t mu_s^T and M = V^T G U, the differential of the SVD gives dL/dH = U Q V^T,
+//   Q_ij = [ M_ij (D_jj s_i - D_ii s_j) - M_ji (D_ii s_i - D_jj s_j) ] / (s_j^2 - s_i^2)   (i != j), Q_ii = 0
+// (for D = I this is -(M_ij - M_ji)/(s_i + s_j): the polar-factor derivative, no s_i - s_j pole).
+// Then dL/ds_n = (dL/dH)(c_n - mu_c) - R^T g_t / N,  dL/dc_n = (dL/dH)^T (s_n - mu_s) + g_t / N.
+// Same numbers as torch autograd through torch.svd on the reference formulation (tests).
+__global__ void __launch_bounds__(SVDH_THREADS) svd_head_tail_bwd_kernel(
+    const float* __restrict__ src, const float* __restrict__ corr, const float* __restrict__ gR,
+    const float* __restrict__ gt, int N, float* __restrict__ g_src, float* __restrict__ g_corr) {
+  __shared__ double red[SVDH_THREADS / 32][15];
+  __shared__ double tot[15];
+  __shared__ float s_gh[9], s_mu[6], s_ds[3], s_dc[3];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* s = src + (size_t)b * 3 * N;
+  const float* c = corr + (size_t)b * 3 * N;
+  double acc[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) acc[i] = 0.0;
+  for (int n = tid; n < N; n += SVDH_THREADS) {
+    const double sv[3] = {(double)s[n], (double)s[N + n], (double)s[2 * N + n]};
+    const double cv[3] = {(double)c[n], (double)c[N + n], (double)c[2 * N + n]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { acc[i] += sv[i]; acc[3 + i] += cv[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[6 + i * 3 + j] += sv[i] * cv[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(L3D_FULL_MASK, acc[i], o);
+    if (lane == 0) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < 15) {
+    double v = 0.0;
+    for (int w = 0; w < SVDH_THREADS / 32; ++w) v += red[w][tid];
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double inv = 1.0 / (double)N;
+    double h[9], fact[22], mu_s[3], mu_c[3];
+    float ms[3], mc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mu_s[i] = tot[i] * inv; mu_c[i] = tot[3 + i] * inv;
+      ms[i] = (float)mu_s[i]; mc[i] = (float)mu_c[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) h[i * 3 + j] = tot[6 + i * 3 + j] - tot[i] * tot[3 + j] * inv;
+    kabsch_from_H(h, ms, mc, nullptr, nullptr, fact);
+    const double* U = fact; const double* V = fact + 9; const double* sg = fact + 18;
+    const double D[3] = {1.0, 1.0, fact[21]};
+    double G[9], g3[3], R[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g3[i] = (double)gt[(size_t)b * 3 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        G[i * 3 + j] = (double)gR[(size_t)b * 9 + i * 3 + j] - g3[i] * mu_s[j];
+        R[i * 3 + j] = V[i * 3 + 0] * D[0] * U[j * 3 + 0] + V[i * 3 + 1] * D[1] * U[j * 3 + 1] + V[i * 3 + 2] * D[2] * U[j * 3 + 2];
+      }
+    double M[9], Q[9], T[9], GH[9];
+    // M = V^T G U
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) T[i * 3 + j] = V[0 * 3 + i] * G[0 * 3 + j] + V[1 * 3 + i] * G[1 * 3 + j] + V[2 * 3 + i] * G[2 * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[i * 3 + j] = T[i * 3 + 0] * U[0 * 3 + j] + T[i * 3 + 1] * U[1 * 3 + j] + T[i * 3 + 2] * U[2 * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (i == j) { Q[i * 3 + j] = 0.0; continue; }
+        const double num = M[i * 3 + j] * (D[j] * sg[i] - D[i] * sg[j]) - M[j * 3 + i] * (D[i] * sg[i] - D[j] * sg[j]);
+        const double den = sg[j] * sg[j] - sg[i] * sg[i];
+        double q;
+        if (D[i] == D[j]) q = -(M[i * 3 + j] - M[j * 3 + i]) / fmax(sg[i] + sg[j], 1e-300);   // pole-free form
+        else q = num / (den != 0.0 ? den : 1e-300);
+        Q[i * 3 + j] = q;
+      }
+    // GH = U Q V^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) T[i * 3 + j] = U[i * 3 + 0] * Q[0 * 3 + j] + U[i * 3 + 1] * Q[1 * 3 + j] + U[i * 3 + 2] * Q[2 * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) GH[i * 3 + j] = T[i * 3 + 0] * V[j * 3 + 0] + T[i * 3 + 1] * V[j * 3 + 1] + T[i * 3 + 2] * V[j * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_gh[i] = (float)GH[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s_mu[i] = ms[i]; s_mu[3 + i] = mc[i];
+      // d mu_s = -R^T g_t, d mu_c = g_t, each spread over the N points
+      s_ds[i] = (float)(-(R[0 * 3 + i] * g3[0] + R[1 * 3 + i] * g3[1] + R[2 * 3 + i] * g3[2]) * inv);
+      s_dc[i] = (float)(g3[i] * inv);
+    }
+  }
+  __syncthreads();
+  float* gs = g_src + (size_t)b * 3 * N;
+  float* gc = g_corr + (size_t)b * 3 * N;
+  for (int n = tid; n < N; n += SVDH_THREADS) {
+    const float sx = s[n] - s_mu[0], sy = s[N + n] - s_mu[1], sz = s[2 * N + n] - s_mu[2];
+    const float cx = c[n] - s_mu[3], cy = c[N + n] - s_mu[4], cz = c[2 * N + n] - s_mu[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      gs[(size_t)i * N + n] = s_gh[i * 3] * cx + s_gh[i * 3 + 1] * cy + s_gh[i * 3 + 2] * cz + s_ds[i];
+      gc[(size_t)i * N + n] = s_gh[i] * sx + s_gh[3 + i] * sy + s_gh[6 + i] * sz + s_dc[i];
+    }
+  }
+}
+
 }  // namespace l3d
 
 using namespace l3d;
@@ -202,6 +340,20 @@ extern "C" int l3d_svd_head_tail(const float* src_dev, const float* src_corr_dev
   if (!src_dev || !src_corr_dev || !R_dev || !t_dev || B < 0 || N < 1) return L3D_ERR_INVALID;
   if (B == 0) return L3D_OK;
   svd_head_tail_kernel<<<B, SVDH_THREADS, 0, (cudaStream_t)stream>>>(src_dev, src_corr_dev, N, R_dev, t_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+extern "C" int l3d_svd_head_tail_backward(const float* src_dev, const float* src_corr_dev,
+                                          const float* grad_R_dev, const float* grad_t_dev, int B, int N,
+                                          float* grad_src_dev, float* grad_src_corr_dev, void* stream) {
+  if (!src_dev || !src_corr_dev || !grad_R_dev || !grad_t_dev || !grad_src_dev || !grad_src_corr_dev ||
+      B < 0 || N < 1)
+    return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  svd_head_tail_bwd_kernel<<<B, SVDH_THREADS, 0, (cudaStream_t)stream>>>(
+      src_dev, src_corr_dev, grad_R_dev, grad_t_dev, N, grad_src_dev, grad_src_corr_dev);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;

@@ -3,7 +3,8 @@
 Same constructor, state_dict key (`reflect`) and forward contract.  The soft-correspondence front
 half (score GEMM, softmax, src_corr GEMM: dense contractions) stays on torch /
 cuBLAS; the tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
-branch (svd.py:38-51) and t — is ONE launch of l3d_svd_head_tail for the whole batch.
+branch (svd.py:38-51) and t — is ONE launch of l3d_svd_head_tail for the whole batch, and its backward
+(the reference trains through torch.svd's autograd) ONE launch of l3d_svd_head_tail_backward.
 """
 import math
 
@@ -22,8 +23,27 @@ class _SVDTail(torch.autograd.Function):
         with _C.on_device(src.device):
             _C.check(_C.lib().l3d_svd_head_tail(_C.ptr(src), _C.ptr(src_corr), B, N, _C.ptr(R),
                                                 _C.ptr(t), _C.stream()), "SVDHead")
-        ctx.mark_non_differentiable(R, t)
+        ctx.save_for_backward(src, src_corr)
         return R, t
+
+    @staticmethod
+    def backward(ctx, grad_R, grad_t):
+        src, src_corr = ctx.saved_tensors
+        B, _, N = src.shape
+        grad_R = (torch.zeros((B, 3, 3), device=src.device) if grad_R is None else grad_R).contiguous().float()
+        grad_t = (torch.zeros((B, 3), device=src.device) if grad_t is None else grad_t).contiguous().float()
+        g_src = torch.empty_like(src)
+        g_corr = torch.empty_like(src_corr)
+        with _C.on_device(src.device):
+            _C.check(_C.lib().l3d_svd_head_tail_backward(_C.ptr(src), _C.ptr(src_corr), _C.ptr(grad_R),
+                                                         _C.ptr(grad_t), B, N, _C.ptr(g_src), _C.ptr(g_corr),
+                                                         _C.stream()), "SVDHead backward")
+        return g_src, g_corr
+
+
+def svd_head_tail(src, src_corr):
+    """src, src_corr [B,3,N] (CUDA fp32) -> R [B,3,3], t [B,3]; differentiable."""
+    return _SVDTail.apply(_C.require_cuda(src, "src"), _C.require_cuda(src_corr, "src_corr"))
 
 
 class SVDHead(nn.Module):
@@ -43,12 +63,4 @@ class SVDHead(nn.Module):
         scores = torch.matmul(src_embedding.transpose(2, 1).contiguous(), tgt_embedding) / math.sqrt(d_k)
         scores = torch.softmax(scores, dim=2)
         src_corr = torch.matmul(tgt, scores.transpose(2, 1).contiguous())
-        if torch.is_grad_enabled() and (src_corr.requires_grad or src.requires_grad):
-            raise NotImplementedError(
-                "learning3d_b200.SVDHead: the differentiable (training) path through the 3x3 SVD is not "
-                "built yet (SURVEY.md §8f); run under torch.no_grad() / eval as examples/test_dcp.py does")
-        src = _C.require_cuda(src, "src")
-        src_corr = _C.require_cuda(src_corr, "src_corr")
-        # NOTE: as in the reference's eval use (examples/test_dcp.py) R, t carry no gradient here; the
-        # differentiable SVD backward is part of the "next" rows (training path).
-        return _SVDTail.apply(src, src_corr)
+        return svd_head_tail(src, src_corr)

@@ -121,3 +121,57 @@ def test_svd_tail_vs_oracle_and_kabsch_entry():
     _C.check(_C.lib().l3d_kabsch3x3_batched(_C.ptr(Hd), _C.ptr(ms), _C.ptr(mc), B, _C.ptr(R2), _C.ptr(t2), _C.stream()))
     torch.cuda.synchronize()
     np.testing.assert_allclose(R2.cpu().numpy(), oR, atol=1e-5)
+
+
+def _torch_tail(src, corr):
+    """utils/svd.py:29-58 in differentiable torch (fp64): the formulation autograd differentiates in the
+    reference's training scripts."""
+    B = src.shape[0]
+    sc = src - src.mean(dim=2, keepdim=True)
+    cc = corr - corr.mean(dim=2, keepdim=True)
+    H = torch.matmul(sc, cc.transpose(2, 1))
+    Rs = []
+    reflect = torch.eye(3, dtype=src.dtype, device=src.device); reflect[2, 2] = -1
+    for i in range(B):
+        u, s, vh = torch.linalg.svd(H[i])
+        v = vh.transpose(0, 1)
+        r = v @ u.transpose(0, 1)
+        if torch.det(r) < 0:
+            r = (v @ reflect) @ u.transpose(0, 1)
+        Rs.append(r)
+    R = torch.stack(Rs)
+    t = torch.matmul(-R, src.mean(dim=2, keepdim=True)) + corr.mean(dim=2, keepdim=True)
+    return R, t.view(B, 3)
+
+
+def test_svd_tail_backward_matches_autograd():
+    from learning3d_b200.utils.svd import svd_head_tail
+    rng = np.random.default_rng(21)
+    B, N = 6, 300
+    src = rng.standard_normal((B, 3, N)).astype(np.float32)
+    A = rng.standard_normal((B, 3, 3)).astype(np.float32)
+    A[3:] *= np.sign(np.linalg.det(A[3:]))[:, None, None] * -1      # items 3..5: reflections -> det fix branch
+    corr = (A @ src + 0.05 * rng.standard_normal((B, 3, N)).astype(np.float32)).astype(np.float32)
+    s = T(src).requires_grad_(True); c = T(corr).requires_grad_(True)
+    R, t = svd_head_tail(s, c)
+    wR = torch.randn_like(R); wt = torch.randn_like(t)
+    ((R * wR).sum() + (t * wt).sum()).backward()
+    s64 = T(src).double().requires_grad_(True); c64 = T(corr).double().requires_grad_(True)
+    R64, t64 = _torch_tail(s64, c64)
+    ((R64 * wR.double()).sum() + (t64 * wt.double()).sum()).backward()
+    np.testing.assert_allclose(R.detach().cpu().numpy(), R64.detach().cpu().numpy(), atol=1e-5)
+    scale = s64.grad.abs().max().item()
+    np.testing.assert_allclose(s.grad.cpu().numpy(), s64.grad.cpu().numpy(), atol=2e-5 * scale + 1e-7)
+    np.testing.assert_allclose(c.grad.cpu().numpy(), c64.grad.cpu().numpy(), atol=2e-5 * scale + 1e-7)
+    assert (np.linalg.det(A[3:]) < 0).all()
+
+
+def test_svd_head_module_is_trainable(golden_dir):
+    from learning3d_b200.utils import SVDHead
+    g = np.load(f"{golden_dir}/svd_head.npz")
+    head = SVDHead(64).to(DEV)
+    e1 = T(g["src_emb"]).requires_grad_(True); e2 = T(g["tgt_emb"]).requires_grad_(True)
+    R, t = head(e1, e2, T(g["src"]), T(g["tgt"]))
+    np.testing.assert_allclose(R.detach().cpu().numpy(), g["R"], atol=1e-5)
+    (R.sum() + t.sum()).backward()
+    assert torch.isfinite(e1.grad).all() and e1.grad.abs().sum() > 0
