@@ -156,9 +156,11 @@ def test_svd_tail_backward_matches_autograd():
     R, t = svd_head_tail(s, c)
     wR = torch.randn_like(R); wt = torch.randn_like(t)
     ((R * wR).sum() + (t * wt).sum()).backward()
-    s64 = T(src).double().requires_grad_(True); c64 = T(corr).double().requires_grad_(True)
+    # reference gradients on the CPU (fp64 LAPACK): torch.linalg.svd on the GPU drags cuSOLVER/MAGMA
+    # initialisation (minutes on a cold box) into the suite
+    s64 = torch.from_numpy(src).double().requires_grad_(True); c64 = torch.from_numpy(corr).double().requires_grad_(True)
     R64, t64 = _torch_tail(s64, c64)
-    ((R64 * wR.double()).sum() + (t64 * wt.double()).sum()).backward()
+    ((R64 * wR.double().cpu()).sum() + (t64 * wt.double().cpu()).sum()).backward()
     np.testing.assert_allclose(R.detach().cpu().numpy(), R64.detach().cpu().numpy(), atol=1e-5)
     scale = s64.grad.abs().max().item()
     np.testing.assert_allclose(s.grad.cpu().numpy(), s64.grad.cpu().numpy(), atol=2e-5 * scale + 1e-7)
