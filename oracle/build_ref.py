@@ -9,8 +9,11 @@ Built here:
     extension (CPU `forward/backward` = nnsearch, and its CUDA kernels `forward_cuda/
     backward_cuda` compiled as ordinary CUDA for sm_100).  The CPU entry points are the
     `"kind": "reference"` baseline and pin oracle/l3d_oracle.c's Chamfer restatement.
-Not buildable (recorded in DESIGN.md): losses/cuda/emd_torch (AT_CHECK / tensor.type() removed
-from torch 2.11) and utils/lib (THC removed) through their own build files.
+  * libpn2_ref.so — utils/lib/src/*_gpu.cu (pointnet2 kernels + launchers) behind ref_shims/pn2_shim.cu.
+  * libemd_ref.so — losses/cuda/emd_torch/pkg/include/cuda/emd.cuh (EMD kernels + launchers) behind
+    ref_shims/emd_shim.cu.
+The extensions' OWN build files do not work any more (emd_torch: AT_CHECK / tensor.type() removed from
+torch 2.11; utils/lib: THC removed): only their kernels/launchers are compiled, in place.
 """
 import os
 import sys
@@ -77,16 +80,42 @@ def build_pointnet2():
     print("built", dst)
 
 
+def build_emd():
+    """losses/cuda/emd_torch/pkg/include/cuda/emd.cuh — the reference's EMD kernels + launchers, included in
+    place by oracle/ref_shims/emd_shim.cu, which only swaps the dispatch macro that no longer compiles
+    (tensor.type()) for a float-only one.  The extension's own host glue (emd.h: AT_CHECK) is not used."""
+    import subprocess
+    import sysconfig
+    import torch
+    from torch.utils.cpp_extension import include_paths
+    inc = os.path.join(REF, "losses", "cuda", "emd_torch", "pkg", "include")
+    shim = os.path.join(HERE, "ref_shims", "emd_shim.cu")
+    dst = os.path.join(OUT, "libemd_ref.so")
+    if _fresh(dst, [shim, os.path.join(inc, "cuda", "emd.cuh"), __file__]):
+        print("up to date: libemd_ref.so")
+        return
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+           "-shared", "-Xcompiler", "-fPIC", "-w", "-I" + inc, "-I" + sysconfig.get_paths()["include"]]
+    cmd += ["-I" + p for p in include_paths()]
+    cmd += ["-o", dst, shim, "-L" + tlib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+            "-Xlinker", "-rpath=" + tlib]
+    subprocess.run(cmd, check=True, env=dict(os.environ, CC="/usr/bin/gcc", CXX="/usr/bin/g++"))
+    print("built", dst)
+
+
 def main():
     if not os.path.isdir(REF):
         print("no /root/reference here: keeping prebuilt oracle/_ref (if any)")
         return 0
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["chamfer", "pointnet2"]
+    which = sys.argv[1:] or ["chamfer", "pointnet2", "emd"]
     if "chamfer" in which:
         build_chamfer()
     if "pointnet2" in which:
         build_pointnet2()
+    if "emd" in which:
+        build_emd()
     return 0
 
 

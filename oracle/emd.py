@@ -66,3 +66,15 @@ def svd_head_tail(src, src_corr):
         R[i] = r
     t = np.matmul(-R, src.mean(axis=2, keepdims=True)) + src_corr.mean(axis=2, keepdims=True)
     return R, t.reshape(B, 3)
+
+
+def ref_emd():
+    """ctypes handle on oracle/_ref/libemd_ref.so — the reference's own EMD CUDA kernels (emd.cuh) behind
+    oracle/ref_shims/emd_shim.cu.  None when not built.  GPU only; import torch first (libtorch symbols)."""
+    import ctypes
+    import os
+    import torch  # noqa: F401
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libemd_ref.so")
+    if not os.path.exists(path):
+        return None
+    return ctypes.CDLL(path)
