@@ -90,6 +90,24 @@ def test_against_reference_cuda_kernels(oracle_mod):
                      _time(lambda: lib.l3d_chamfer_backward(_C.ptr(a), _C.ptr(b), Bc, 1024, 1024, _C.ptr(g1), _C.ptr(g2),
                                                             _C.ptr(j1), _C.ptr(j2), _C.ptr(ga), _C.ptr(gb), s))))
 
+    # EMD (C5): the reference's approxmatch + matchcost / matchcostgrad kernels
+    from oracle import emd as oemd
+    remd = oemd.ref_emd()
+    if remd is not None:
+        Be, ne = 8, 1024
+        a = torch.rand(Be, ne, 3, device=DEV); b = torch.rand(Be, ne, 3, device=DEV)
+        rm = torch.zeros(Be, ne, ne, device=DEV); rt = torch.zeros(Be, 4 * ne, device=DEV); rc = torch.zeros(Be, device=DEV)
+        m = torch.empty(Be, ne, ne, device=DEV); c = torch.empty(Be, device=DEV)
+        ws = torch.empty(int(lib.l3d_emd_forward_ws_bytes(Be, ne, ne)), dtype=torch.uint8, device=DEV)
+        rows.append(("EMD forward B8 N1024 (approxmatch+matchcost)",
+                     _time(lambda: remd.ref_emd_forward(Be, ne, ne, _p(a), _p(b), _p(rm), _p(rt), _p(rc)), 5, 1),
+                     _time(lambda: lib.l3d_emd_forward(_C.ptr(a), _C.ptr(b), Be, ne, ne, _C.ptr(c), _C.ptr(m), _C.ptr(ws), s), 5, 1)))
+        g1 = torch.empty_like(a); g2 = torch.empty_like(b)
+        ws2 = torch.empty(int(lib.l3d_emd_backward_ws_bytes(Be, ne, ne)), dtype=torch.uint8, device=DEV)
+        rows.append(("EMD backward B8 N1024",
+                     _time(lambda: remd.ref_emd_backward(Be, ne, ne, _p(a), _p(b), _p(rm), _p(g1), _p(g2)), 5, 1),
+                     _time(lambda: lib.l3d_emd_backward(_C.ptr(a), _C.ptr(b), _C.ptr(rm), Be, ne, ne, _C.ptr(g1), _C.ptr(g2), _C.ptr(ws2), s), 5, 1)))
+
     # kNN graph (C2): the reference's torch op sequence on the same GPU
     from oracle import ref_torch
     from learning3d_b200.utils import knn
