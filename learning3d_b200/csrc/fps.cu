@@ -6,15 +6,18 @@
 //
 // FPS is inherently sequential (npoint dependent rounds), so it is latency bound: one CTA per batch
 // item keeps every point and its running min-distance in REGISTERS for the whole run, and a round
-// costs one distance update per register, one shuffle arg-max, ONE __syncthreads (double-buffered
-// per-warp results) and a redundant per-warp final reduce — no global-memory traffic inside the loop
-// except the 12-byte read of the newly selected point (L1-resident).
+// costs one distance update per register, one REDUX (__reduce_max_sync) warp arg-max on the distance
+// bits plus a tie-key pass, ONE __syncthreads (double-buffered per-warp results) and a redundant
+// per-warp final reduce — no global-memory traffic inside the loop except the 12-byte read of the newly
+// selected point (L1-resident).
 //
 // Selection semantics reproduced exactly (indices are bit-identical on tie-free AND tied inputs):
 //   mode 0 (pointnet2 CUDA): d = nvcc-contracted fma form; per-thread strict '>' over k = tid, tid+bs, ...;
 //           tree reduce keeps the LEFT (lower tid) entry on ties (sampling_gpu.cu:86-91,136-137):
-//           the winner among equal distances is the smallest (k mod bs, k), bs = the reference's
-//           block size 2^floor(log2 n) <= 1024 (cuda_utils.h:10-14);
+//           the tree pairs tid with tid+stride for stride = bs/2 .. 1, so among equal distances the winner
+//           is the smallest (bit-reversed (k mod bs) over log2 bs bits, then k), bs = the reference's
+//           block size 2^floor(log2 n) <= 1024 (cuda_utils.h:10-14) — oracle/l3d_oracle_group.c simulates
+//           the tree literally and the two agree on lattice clouds (tests/test_gpu_fuzz.py);
 //   mode 1 (torch): d = (dx*dx + dy*dy) + dz*dz rounded; torch.max returns the first maximal index.
 #include "common.cuh"
 #include "../../include/l3d_b200.h"

@@ -6,17 +6,21 @@
 //   knn_point()                 utils/model_common_utils.py:84-100   (MODE_DIRECT_RN)
 //   pointnet2 knn / three_nn    utils/lib/src/interpolate_gpu.cu:9-57,81-124 (MODE_DIRECT_FMA)
 //
-// Design (one warp per query row):
+// Design:
 //   1. the candidate cloud of batch item b is bulk-copied (cp.async.bulk + mbarrier) into
 //      shared memory once per CTA and repacked to float4 (x, y, z, |p|^2);
-//   2. per row each lane evaluates 32 candidates per 1024-candidate tile into registers;
-//   3. lane-group maxima are bitonic-sorted across the warp: the k-th largest group maximum
-//      T0 is a proven lower bound of the k-th best key, so only keys >= T0 (about 1.5k of
-//      them) are compacted into a small shared-memory buffer;
-//   4. the survivors are bitonic-sorted by (key desc, index asc) and the first k written
-//      out with one coalesced store per row.
-//   A row whose survivors overflow the buffer (duplicate points, adversarial ties) is redone
-//   by an exact k-round arg-max scan, so the result is always the full (key, index) order.
+//   2. a warp owns KNN_R = 2 query rows at a time (k <= 24: knn_rows_v2) and each lane evaluates
+//      32 candidates per 1024-candidate tile into registers, the candidate float4 shared by both rows;
+//   3. the per-lane maxima are sorted across the warp: the k-th largest lane maximum T0 is a proven
+//      lower bound of the k-th best key, so only keys >= T0 (about 1.5 k of them, found from the sign
+//      bit of key - T0) survive; they are re-evaluated from shared memory into 64-bit composites
+//      (order-preserving key bits << 32 | ~index), one or two per lane;
+//   4. a flip + half-cleaner shuffle network sorts the composites (key desc, index asc) and the first
+//      k are written with one coalesced store per row.
+//   Larger k uses the generic knn_row<MODE,KS> (KS survivors per lane in shared memory); clouds with
+//   N <= 256 and k*8 >= N sort the whole row in registers (knn_row_sort).  A row whose survivors
+//   overflow (duplicate points, adversarial ties) is redone by an exact k-round arg-max scan
+//   (knn_row_slow), so the result is always the full (key, index) order.
 #include "common.cuh"
 #include "../../include/l3d_b200.h"
 #include "launch_count.h"
