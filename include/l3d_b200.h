@@ -274,6 +274,25 @@ int l3d_svd_head_tail_backward(const float* src_dev, const float* src_corr_dev, 
                                const float* grad_t_dev, int B, int N, float* grad_src_dev,
                                float* grad_src_corr_dev, void* stream);
 
+/*
+ * Front half of SVDHead.forward (utils/svd.py:23-28), fused, forward only:
+ *   scores = softmax(src_emb^T . tgt_emb / sqrt(D), dim=2);  src_corr = tgt_xyz . scores^T
+ * src_emb_dev [B,D,Ns], tgt_emb_dev [B,D,Nt], tgt_xyz_dev [B,3,Nt] -> src_corr_dev [B,3,Ns], all fp32.
+ * The [B,Ns,Nt] score matrix is never written: tcgen05 3xTF32 GEMM tiles in TMEM + online softmax.
+ * Tolerance vs the reference's fp32 matmul/softmax: 2e-5 absolute on src_corr (tests/test_gpu_softcorr.py).
+ */
+int l3d_soft_correspondence(const float* src_emb_dev, const float* tgt_emb_dev, const float* tgt_xyz_dev,
+                            int B, int D, int Ns, int Nt, float* src_corr_dev, void* stream);
+/* Test/debug aid: synchronises the device and returns the pipeline status word of
+ * l3d_soft_correspondence (0 = ok, 1/2/3 = a bounded mbarrier wait of the epilogue / producer /
+ * MMA-issuer role ran out), or a CUDA error code. */
+int l3d_soft_correspondence_status(void);
+/* Debug variant of l3d_soft_correspondence that also dumps the raw score accumulators
+ * (src_emb^T . tgt_emb, before the 1/sqrt(D) scaling) to scores_dev [B,Ns,Nt]; used by the GEMM parity test. */
+int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* tgt_emb_dev,
+                                         const float* tgt_xyz_dev, int B, int D, int Ns, int Nt,
+                                         float* src_corr_dev, float* scores_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

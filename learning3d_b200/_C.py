@@ -52,6 +52,9 @@ _SIGNATURES = {
     "l3d_kabsch3x3_batched": [_P, _P, _P, _I, _P, _P, _P],
     "l3d_svd_head_tail": [_P, _P, _I, _I, _P, _P, _P],
     "l3d_svd_head_tail_backward": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "l3d_soft_correspondence": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "l3d_soft_correspondence_status": [],
+    "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "l3d_chamfer_ws_bytes": [_I, _I, _I],

@@ -1,0 +1,412 @@
+// Soft correspondences of DCP's SVD head, fused (sm_100a: tcgen05 + TMEM).
+//
+// Replaces utils/svd.py:23-28:
+//     scores   = softmax(src_emb^T . tgt_emb / sqrt(d_k), dim=2)      [B, Ns, Nt]   (134 MB at C3)
+//     src_corr = tgt . scores^T                                        [B, 3, Ns]
+// without ever writing the score matrix: one CTA owns 128 source points, walks the target points
+// in blocks of 128, and keeps a running (max, sum, sum*xyz) per source point — the flash-attention
+// recurrence with a 3-wide V.
+//
+// Arithmetic: the score GEMM runs on the 5th-gen tensor cores as 3xTF32 — every fp32 operand x is
+// split into hi = rna_tf32(x) and lo = x - hi (exact), and  a.b ~= hi.hi + hi.lo + lo.hi  accumulated
+// in fp32 in TMEM: relative error ~2^-21 per product, the same class as the fp32 SGEMM the reference
+// calls (torch.matmul with TF32 off).  exp() is ex2.approx on log2(e)-prescaled scores.
+//
+// Roles (288 threads, 1 CTA / SM):
+//   warps 0-3  epilogue: tcgen05.ld the 128x128 score tile (lane = source point), online softmax,
+//              xyz accumulation; double-buffered accumulators so they overlap the next tile's MMAs
+//   warps 4-7  producers: coalesced fp32 loads of the [d, n]-major embeddings, hi/lo split, transposed
+//              128B-swizzled K-major stores (conflict-free STS.128), fence.proxy.async, mbarrier arrive
+//   warp  8    one thread issues tcgen05.mma (M128 N128 K8, kind::tf32) and tcgen05.commit
+// Every mbarrier wait is bounded: a protocol bug surfaces as an error code, never as a hung GPU.
+#include "common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+#include <math.h>
+
+namespace l3d {
+
+constexpr int SC_BM = 128;                 // source points per CTA  (UMMA M)
+constexpr int SC_BN = 128;                 // target points per tile (UMMA N)
+constexpr int SC_BK = 32;                  // embedding channels per stage: 32 x 4 B = one 128 B swizzle row
+constexpr int SC_UK = 8;                   // UMMA K for kind::tf32 (32 bytes)
+constexpr int SC_STAGES = 3;
+constexpr int SC_TILE_BYTES = SC_BM * SC_BK * 4;       // 16 KB per operand tile
+constexpr int SC_STAGE_BYTES = 4 * SC_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int SC_EPI_THREADS = 128;
+constexpr int SC_PROD_THREADS = 128;
+constexpr int SC_THREADS = SC_EPI_THREADS + SC_PROD_THREADS + 32;
+constexpr int SC_TMEM_COLS = 2 * SC_BN;    // two fp32 accumulators
+constexpr uint32_t SC_SPIN_LIMIT = 1u << 22;
+
+struct SoftCorrParams {
+  const float* src_emb;   // [B, D, Ns]
+  const float* tgt_emb;   // [B, D, Nt]
+  const float* tgt_xyz;   // [B, 3, Nt]
+  float* out;             // [B, 3, Ns]
+  float* dbg_scores;      // optional [B, Ns, Nt]: raw accumulator dump (debug entry point only)
+  int* err;               // device error word (0 = ok)
+  int B, D, Ns, Nt;
+  float c;                // log2(e) / sqrt(D)
+};
+
+struct SoftCorrShared {
+  float4 xyz[2][SC_BN];
+  uint64_t full[SC_STAGES];
+  uint64_t empty[SC_STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  int failed;
+};
+
+__device__ int g_softcorr_error = 0;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < SC_SPIN_LIMIT; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp reads TMEM lane (warp%4)*32 + t
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
+// rows of 128 B, 8-row groups 1024 B apart (SBO), 16-byte chunk index XOR (row & 7).
+__device__ __forceinline__ uint64_t sc_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset       bits [32,46)
+  d |= (uint64_t)1 << 46;                      // descriptor version 1     bits [46,48)
+  d |= (uint64_t)2 << 61;                      // layout = SWIZZLE_128B    bits [61,64)
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+constexpr uint32_t SC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SC_BN >> 3) << 17) |
+                              ((uint32_t)(SC_BM >> 4) << 24);
+
+// byte offset of element (row r, 16-byte chunk c) inside a [128 x 32 fp32] swizzled tile
+__device__ __forceinline__ uint32_t sc_swz(int r, int c) {
+  return (uint32_t)(((r >> 3) << 10) | ((r & 7) << 7) | ((c ^ (r & 7)) << 4));
+}
+
+// one operand row (32 channels of one point) -> registers; out-of-range -> 0
+__device__ __forceinline__ void sc_load_row(const float* __restrict__ base, int D, int N, int d0,
+                                            int n, float (&v)[SC_BK]) {
+  const bool nv = n < N;
+  const float* p = base + (size_t)d0 * N + (nv ? n : 0);
+#pragma unroll
+  for (int dd = 0; dd < SC_BK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + (size_t)dd * N) : 0.f;
+}
+// split into tf32 hi / lo and store the row transposed into the two swizzled tiles
+__device__ __forceinline__ void sc_store_row(unsigned char* hi_tile, unsigned char* lo_tile, int r,
+                                             const float (&v)[SC_BK]) {
+#pragma unroll
+  for (int c = 0; c < SC_BK / 4; ++c) {
+    uint4 h, l;
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x = v[c * 4 + e];
+      const uint32_t hb = rna_tf32(x);
+      hp[e] = hb;
+      lp[e] = __float_as_uint(__fsub_rn(x, __uint_as_float(hb)));
+    }
+    const uint32_t off = sc_swz(r, c);
+    *reinterpret_cast<uint4*>(hi_tile + off) = h;
+    *reinterpret_cast<uint4*>(lo_tile + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrParams p) {
+  extern __shared__ unsigned char sc_raw[];
+  // 1024-byte alignment: the swizzle XOR is applied to absolute shared addresses
+  unsigned char* tiles = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(sc_raw) + 1023) & ~(uintptr_t)1023);
+  SoftCorrShared* sh = reinterpret_cast<SoftCorrShared*>(tiles + SC_STAGES * SC_STAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * SC_BM;
+  const int num_jb = (p.Nt + SC_BN - 1) / SC_BN;
+  const int num_kb = (p.D + SC_BK - 1) / SC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&sh->full[s], SC_PROD_THREADS); mbar_init(&sh->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS); }
+    sh->failed = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&sh->tmem_base)),
+                 "n"(SC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------ epilogue: online softmax over target tiles
+    const int i = i0 + tid;
+    const float c = p.c;
+    float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    bool ok = true;
+    for (int jb = 0; jb < num_jb && ok; ++jb) {
+      const int a = jb & 1;
+      const int j0 = jb * SC_BN;
+      {
+        const int j = j0 + tid;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < p.Nt) {
+          const float* t = p.tgt_xyz + (size_t)b * 3 * p.Nt + j;
+          q = make_float4(__ldg(t), __ldg(t + p.Nt), __ldg(t + 2 * (size_t)p.Nt), 0.f);
+        }
+        sh->xyz[a][tid] = q;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!mbar_wait_bounded(&sh->acc_full[a], (uint32_t)((jb >> 1) & 1))) { ok = false; break; }
+      __syncwarp();
+      tc_fence_after();
+      const int nvalid = min(SC_BN, p.Nt - j0);
+#pragma unroll 1
+      for (int ch = 0; ch < SC_BN / 32; ++ch) {
+        float v[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * SC_BN + ch * 32), v);
+        if (p.dbg_scores && i < p.Ns) {
+          for (int e = 0; e < 32; ++e)
+            if (j0 + ch * 32 + e < p.Nt) p.dbg_scores[((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32 + e] = v[e];
+        }
+        if (ch * 32 >= nvalid) continue;
+        if (nvalid - ch * 32 < 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (ch * 32 + e >= nvalid) v[e] = -INFINITY;
+        }
+        float cm = v[0];
+#pragma unroll
+        for (int e = 1; e < 32; ++e) cm = fmaxf(cm, v[e]);
+        const float m_new = fmaxf(m, __fmul_rn(cm, c));
+        const float alpha = ex2_approx(__fsub_rn(m, m_new));
+        l = __fmul_rn(l, alpha); ax = __fmul_rn(ax, alpha); ay = __fmul_rn(ay, alpha); az = __fmul_rn(az, alpha);
+        m = m_new;
+        const float4* xz = &sh->xyz[a][ch * 32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float pe = ex2_approx(fmaf(v[e], c, -m));
+          const float4 q = xz[e];
+          l = __fadd_rn(l, pe);
+          ax = fmaf(pe, q.x, ax); ay = fmaf(pe, q.y, ay); az = fmaf(pe, q.z, az);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->acc_empty[a]);
+    }
+    if (!ok) { sh->failed = 1; atomicCAS(p.err, 0, 1); }
+    if (ok && i < p.Ns) {
+      const float inv = __fdividef(1.f, l);
+      float* o = p.out + (size_t)b * 3 * p.Ns + i;
+      o[0] = __fmul_rn(ax, inv);
+      o[p.Ns] = __fmul_rn(ay, inv);
+      o[2 * (size_t)p.Ns] = __fmul_rn(az, inv);
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------ producers
+    const int r = tid - SC_EPI_THREADS;          // tile row owned by this thread (A and B)
+    const float* A = p.src_emb + (size_t)b * p.D * p.Ns;
+    const float* Bm = p.tgt_emb + (size_t)b * p.D * p.Nt;
+    const int total = num_jb * num_kb;
+    // Two register sets, loop unrolled by two: the rows of stage it+1 are requested BEFORE stage it is
+    // converted and stored, so their L2 latency overlaps ~300 instructions of split/STS work (and the
+    // wait for a free stage when the tensor core is the bottleneck).
+    float va[SC_BK], vb[SC_BK], wa[SC_BK], wb[SC_BK];
+    bool ok = true;
+    auto step = [&](int it, float (&ca)[SC_BK], float (&cb)[SC_BK], float (&na)[SC_BK], float (&nb)[SC_BK]) {
+      if (it + 1 < total) {
+        const int njb = (it + 1) / num_kb, nkb = (it + 1) - njb * num_kb;
+        sc_load_row(A, p.D, p.Ns, nkb * SC_BK, i0 + r, na);
+        sc_load_row(Bm, p.D, p.Nt, nkb * SC_BK, njb * SC_BN + r, nb);
+      }
+      const int s = it % SC_STAGES;
+      const uint32_t n = (uint32_t)(it / SC_STAGES);
+      unsigned char* st = tiles + s * SC_STAGE_BYTES;
+      if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; return; }
+      sc_store_row(st, st + SC_TILE_BYTES, r, ca);
+      sc_store_row(st + 2 * SC_TILE_BYTES, st + 3 * SC_TILE_BYTES, r, cb);
+      fence_proxy_async();
+      mbar_arrive(&sh->full[s]);
+    };
+    sc_load_row(A, p.D, p.Ns, 0, i0 + r, va);
+    sc_load_row(Bm, p.D, p.Nt, 0, r, vb);
+    for (int it = 0; it < total && ok; it += 2) {
+      step(it, va, vb, wa, wb);
+      if (it + 1 < total && ok) step(it + 1, wa, wb, va, vb);
+    }
+    if (!ok) { sh->failed = 1; atomicCAS(p.err, 0, 2); }
+  } else {
+    // ------------------------------------------------ MMA issuer
+    bool ok = true;
+    int it = 0;
+    for (int jb = 0; jb < num_jb && ok; ++jb) {
+      const int a = jb & 1;
+      if (!mbar_wait_bounded(&sh->acc_empty[a], (uint32_t)(((jb >> 1) & 1) ^ 1))) { ok = false; break; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + (uint32_t)(a * SC_BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % SC_STAGES;
+        const uint32_t n = (uint32_t)(it / SC_STAGES);
+        if (!mbar_wait_bounded(&sh->full[s], n & 1u)) { ok = false; break; }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(tiles + s * SC_STAGE_BYTES);
+          const uint64_t a_hi = sc_smem_desc(sa), a_lo = sc_smem_desc(sa + SC_TILE_BYTES);
+          const uint64_t b_hi = sc_smem_desc(sa + 2 * SC_TILE_BYTES), b_lo = sc_smem_desc(sa + 3 * SC_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < SC_BK / SC_UK; ++k) {
+            const uint64_t adv = (uint64_t)((k * SC_UK * 4) >> 4);   // +32 bytes along K inside the swizzle row
+            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, SC_IDESC, (kb | k) != 0);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, SC_IDESC, 1u);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, SC_IDESC, 1u);
+          }
+          tc_commit(&sh->empty[s]);
+          if (kb == num_kb - 1) tc_commit(&sh->acc_full[a]);
+        }
+        __syncwarp();
+      }
+    }
+    if (!ok && lane == 0) { sh->failed = 1; atomicCAS(p.err, 0, 3); }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+size_t softcorr_smem_bytes() { return (size_t)SC_STAGES * SC_STAGE_BYTES + sizeof(SoftCorrShared) + 1024; }
+
+}  // namespace l3d
+
+using namespace l3d;
+
+static int softcorr_launch(const float* src_emb, const float* tgt_emb, const float* tgt_xyz, int B, int D,
+                           int Ns, int Nt, float* src_corr, float* dbg_scores, void* stream) {
+  if (B < 0 || D < 0 || Ns < 0 || Nt < 0) return L3D_ERR_INVALID;
+  if (B == 0 || Ns == 0) return L3D_OK;
+  if (!src_emb || !tgt_emb || !tgt_xyz || !src_corr) return L3D_ERR_INVALID;
+  if (Nt == 0 || D == 0) return L3D_ERR_INVALID;      // softmax over an empty row is undefined
+  if (B > 65535) return L3D_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  const size_t smem = softcorr_smem_bytes();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  SoftCorrParams p;
+  p.src_emb = src_emb; p.tgt_emb = tgt_emb; p.tgt_xyz = tgt_xyz; p.out = src_corr; p.dbg_scores = dbg_scores;
+  p.B = B; p.D = D; p.Ns = Ns; p.Nt = Nt;
+  p.c = (float)(1.4426950408889634 / sqrt((double)D));
+  void* errp = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&errp, g_softcorr_error);
+  if (e != cudaSuccess) return (int)e;
+  p.err = (int*)errp;
+  dim3 grid((Ns + SC_BM - 1) / SC_BM, B);
+  softcorr_kernel<<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+extern "C" int l3d_soft_correspondence(const float* src_emb, const float* tgt_emb, const float* tgt_xyz,
+                                       int B, int D, int Ns, int Nt, float* src_corr, void* stream) {
+  return softcorr_launch(src_emb, tgt_emb, tgt_xyz, B, D, Ns, Nt, src_corr, nullptr, stream);
+}
+
+// Debug variant: additionally dumps the raw (unscaled) score accumulators to scores_dev [B,Ns,Nt].
+extern "C" int l3d_debug_soft_correspondence_scores(const float* src_emb, const float* tgt_emb,
+                                                    const float* tgt_xyz, int B, int D, int Ns, int Nt,
+                                                    float* src_corr, float* scores_dev, void* stream) {
+  if (!scores_dev) return L3D_ERR_INVALID;
+  return softcorr_launch(src_emb, tgt_emb, tgt_xyz, B, D, Ns, Nt, src_corr, scores_dev, stream);
+}
+
+// Synchronises the device and returns the pipeline error word of l3d_soft_correspondence
+// (0 = ok; 1/2/3 = an epilogue / producer / MMA-issuer wait ran out).  Test and debug aid.
+extern "C" int l3d_soft_correspondence_status(void) {
+  int v = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyFromSymbol(&v, g_softcorr_error, sizeof(int));
+  if (e != cudaSuccess) return (int)e;
+  return v;
+}
