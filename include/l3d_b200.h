@@ -287,6 +287,9 @@ int l3d_soft_correspondence(const float* src_emb_dev, const float* tgt_emb_dev, 
  * l3d_soft_correspondence (0 = ok, 1/2/3 = a bounded mbarrier wait of the epilogue / producer /
  * MMA-issuer role ran out), or a CUDA error code. */
 int l3d_soft_correspondence_status(void);
+/* Testing hook: nonzero forces the generic (LDG producer, any shape) operand pipeline even when the
+ * shape is eligible for the TMA pipeline (Ns, Nt multiples of 4, 16-byte aligned embeddings). */
+void l3d_debug_soft_correspondence_force_generic(int on);
 /* Debug variant of l3d_soft_correspondence that also dumps the raw score accumulators
  * (src_emb^T . tgt_emb, before the 1/sqrt(D) scaling) to scores_dev [B,Ns,Nt]; used by the GEMM parity test. */
 int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* tgt_emb_dev,

@@ -1,4 +1,4 @@
-// Soft correspondences of DCP's SVD head, fused (sm_100a: tcgen05 + TMEM).
+// Soft correspondences of DCP's SVD head, fused (sm_100a: TMA + tcgen05 + TMEM).
 //
 // Replaces utils/svd.py:23-28:
 //     scores   = softmax(src_emb^T . tgt_emb / sqrt(d_k), dim=2)      [B, Ns, Nt]   (134 MB at C3)
@@ -8,35 +8,44 @@
 // recurrence with a 3-wide V.
 //
 // Arithmetic: the score GEMM runs on the 5th-gen tensor cores as 3xTF32 — every fp32 operand x is
-// split into hi = rna_tf32(x) and lo = x - hi (exact), and  a.b ~= hi.hi + hi.lo + lo.hi  accumulated
-// in fp32 in TMEM: relative error ~2^-21 per product, the same class as the fp32 SGEMM the reference
-// calls (torch.matmul with TF32 off).  exp() is ex2.approx on log2(e)-prescaled scores.
+// split into hi + lo,  a.b ~= hi.hi + hi.lo + lo.hi  accumulated in fp32 in TMEM: relative error
+// ~2^-21 per product, the same class as the fp32 SGEMM the reference calls (torch.matmul with TF32
+// off).  exp() is ex2.approx on log2(e)-prescaled scores.
 //
-// Roles (288 threads, 1 CTA / SM):
+// Two operand pipelines, one epilogue / MMA structure:
+//   TMA path (Ns, Nt multiples of 4, 16-byte aligned bases — every shape the models produce):
+//     the embeddings are [d, n]-major in HBM, which IS an MN-major UMMA operand: 3-D tensor-map TMA
+//     drops [32 d x 32 n] boxes 128B-swizzled straight into shared memory and the tensor core reads
+//     them as the hi operand (the hardware ignores the low 13 mantissa bits); four "splitter" warps
+//     only derive the lo tiles (x - trunc(x), tf32-rounded) shared-to-shared.  No thread touches
+//     global memory for the GEMM operands.
+//   generic path (any shape): four producer warps load rows with LDG, split, and store K-major
+//     swizzled tiles themselves.
 //   warps 0-3  epilogue: tcgen05.ld the 128x128 score tile (lane = source point), online softmax,
-//              xyz accumulation; double-buffered accumulators so they overlap the next tile's MMAs
-//   warps 4-7  producers: coalesced fp32 loads of the [d, n]-major embeddings, hi/lo split, transposed
-//              128B-swizzled K-major stores (conflict-free STS.128), fence.proxy.async, mbarrier arrive
+//              xyz accumulation; two accumulators in TMEM so it overlaps the next tile's MMAs
+//   warps 4-7  splitters / producers
 //   warp  8    one thread issues tcgen05.mma (M128 N128 K8, kind::tf32) and tcgen05.commit
+//   warp  9    one thread issues the TMA loads (TMA path)
 // Every mbarrier wait is bounded: a protocol bug surfaces as an error code, never as a hung GPU.
 #include "common.cuh"
 #include "../../include/l3d_b200.h"
 #include "launch_count.h"
 
+#include <cuda.h>
 #include <math.h>
 
 namespace l3d {
 
 constexpr int SC_BM = 128;                 // source points per CTA  (UMMA M)
 constexpr int SC_BN = 128;                 // target points per tile (UMMA N)
-constexpr int SC_BK = 32;                  // embedding channels per stage: 32 x 4 B = one 128 B swizzle row
+constexpr int SC_BK = 32;                  // embedding channels per stage
 constexpr int SC_UK = 8;                   // UMMA K for kind::tf32 (32 bytes)
 constexpr int SC_STAGES = 3;
 constexpr int SC_TILE_BYTES = SC_BM * SC_BK * 4;       // 16 KB per operand tile
 constexpr int SC_STAGE_BYTES = 4 * SC_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int SC_EPI_THREADS = 128;
 constexpr int SC_PROD_THREADS = 128;
-constexpr int SC_THREADS = SC_EPI_THREADS + SC_PROD_THREADS + 32;
+constexpr int SC_THREADS = SC_EPI_THREADS + SC_PROD_THREADS + 64;   // + MMA warp + TMA warp
 constexpr int SC_TMEM_COLS = 2 * SC_BN;    // two fp32 accumulators
 constexpr uint32_t SC_SPIN_LIMIT = 1u << 22;
 
@@ -53,12 +62,12 @@ struct SoftCorrParams {
 
 struct SoftCorrShared {
   float4 xyz[2][SC_BN];
-  uint64_t full[SC_STAGES];
-  uint64_t empty[SC_STAGES];
+  uint64_t tma_full[SC_STAGES];   // TMA path: raw tiles landed
+  uint64_t full[SC_STAGES];       // all four operand tiles of the stage are ready for the MMA
+  uint64_t empty[SC_STAGES];      // the MMAs reading the stage have completed
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  int failed;
 };
 
 __device__ int g_softcorr_error = 0;
@@ -126,33 +135,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
+// tf32 rounding (nearest, ties away) on the bit pattern: two integer instructions
+__device__ __forceinline__ uint32_t rna_tf32_bits(uint32_t u) { return (u + 0x1000u) & 0xffffe000u; }
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
-// rows of 128 B, 8-row groups 1024 B apart (SBO), 16-byte chunk index XOR (row & 7).
-__device__ __forceinline__ uint64_t sc_smem_desc(uint32_t saddr) {
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor, sm_100 "version 1"), SWIZZLE_128B.
+//   K-major  (generic path): rows of 32 fp32 (128 B), 8-row groups 1024 B apart (SBO).
+//   MN-major (TMA path): 128 B of n per channel row, 8-channel groups 1024 B apart (SBO), the next
+//            32 points 4096 B further (LBO).
+__device__ __forceinline__ uint64_t sc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address            bits [0,14)
-  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset       bits [32,46)
-  d |= (uint64_t)1 << 46;                      // descriptor version 1     bits [46,48)
-  d |= (uint64_t)2 << 61;                      // layout = SWIZZLE_128B    bits [61,64)
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address            bits [0,14)
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;           // leading byte offset      bits [16,30)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset       bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version 1     bits [46,48)
+  d |= (uint64_t)2 << 61;                          // layout = SWIZZLE_128B    bits [61,64)
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
-constexpr uint32_t SC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SC_BN >> 3) << 17) |
-                              ((uint32_t)(SC_BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = 128
+constexpr uint32_t SC_IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SC_BN >> 3) << 17) |
+                                ((uint32_t)(SC_BM >> 4) << 24);
+constexpr uint32_t SC_IDESC_MN = SC_IDESC_K | (1u << 15) | (1u << 16);   // a_major = b_major = MN
 
-// byte offset of element (row r, 16-byte chunk c) inside a [128 x 32 fp32] swizzled tile
+// byte offset of (row r, 16-byte chunk c) inside a K-major [128 x 32 fp32] swizzled tile
 __device__ __forceinline__ uint32_t sc_swz(int r, int c) {
   return (uint32_t)(((r >> 3) << 10) | ((r & 7) << 7) | ((c ^ (r & 7)) << 4));
 }
 
-// one operand row (32 channels of one point) -> registers; out-of-range -> 0
+// ---- generic producer helpers -------------------------------------------------------------------
 __device__ __forceinline__ void sc_load_row(const float* __restrict__ base, int D, int N, int d0,
                                             int n, float (&v)[SC_BK]) {
   const bool nv = n < N;
@@ -160,44 +187,47 @@ __device__ __forceinline__ void sc_load_row(const float* __restrict__ base, int 
 #pragma unroll
   for (int dd = 0; dd < SC_BK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + (size_t)dd * N) : 0.f;
 }
-// split into tf32 hi / lo and store the row transposed into the two swizzled tiles
-__device__ __forceinline__ void sc_store_row(unsigned char* hi_tile, unsigned char* lo_tile, int r,
-                                             const float (&v)[SC_BK]) {
+__device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile, int r, const float (&v)[SC_BK]) {
 #pragma unroll
   for (int c = 0; c < SC_BK / 4; ++c) {
-    uint4 h, l;
-    uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
-    uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+    uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float x = v[c * 4 + e];
-      const uint32_t hb = rna_tf32(x);
-      hp[e] = hb;
-      lp[e] = __float_as_uint(__fsub_rn(x, __uint_as_float(hb)));
+      h[e] = rna_tf32_bits(__float_as_uint(x));
+      l[e] = __float_as_uint(__fsub_rn(x, __uint_as_float(h[e])));
     }
     const uint32_t off = sc_swz(r, c);
-    *reinterpret_cast<uint4*>(hi_tile + off) = h;
-    *reinterpret_cast<uint4*>(lo_tile + off) = l;
+    sts128(hi_tile + off, make_uint4(h[0], h[1], h[2], h[3]));
+    sts128(lo_tile + off, make_uint4(l[0], l[1], l[2], l[3]));
   }
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrParams p) {
+template <bool USE_TMA>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap_a,
+                const __grid_constant__ CUtensorMap tmap_b) {
   extern __shared__ unsigned char sc_raw[];
   // 1024-byte alignment: the swizzle XOR is applied to absolute shared addresses
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(sc_raw) + 1023) & ~(uintptr_t)1023);
   SoftCorrShared* sh = reinterpret_cast<SoftCorrShared*>(tiles + SC_STAGES * SC_STAGE_BYTES);
+  const uint32_t tiles_s = smem_u32(tiles);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * SC_BM;
   const int num_jb = (p.Nt + SC_BN - 1) / SC_BN;
   const int num_kb = (p.D + SC_BK - 1) / SC_BK;
+  const int total = num_jb * num_kb;
 
   if (tid == 0) {
-    for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&sh->full[s], SC_PROD_THREADS); mbar_init(&sh->empty[s], 1); }
+    for (int s = 0; s < SC_STAGES; ++s) {
+      mbar_init(&sh->tma_full[s], 1);
+      mbar_init(&sh->full[s], SC_PROD_THREADS);
+      mbar_init(&sh->empty[s], 1);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS); }
-    sh->failed = 0;
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -218,7 +248,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
     const float c = p.c;
     float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     bool ok = true;
-    for (int jb = 0; jb < num_jb && ok; ++jb) {
+    for (int jb = 0; jb < num_jb; ++jb) {
       const int a = jb & 1;
       const int j0 = jb * SC_BN;
       {
@@ -268,7 +298,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
       tc_fence_before();
       mbar_arrive(&sh->acc_empty[a]);
     }
-    if (!ok) { sh->failed = 1; atomicCAS(p.err, 0, 1); }
+    if (!ok) atomicCAS(p.err, 0, 1);
     if (ok && i < p.Ns) {
       const float inv = __fdividef(1.f, l);
       float* o = p.out + (size_t)b * 3 * p.Ns + i;
@@ -277,39 +307,54 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
       o[2 * (size_t)p.Ns] = __fmul_rn(az, inv);
     }
   } else if (warp < 8) {
-    // ------------------------------------------------ producers
-    const int r = tid - SC_EPI_THREADS;          // tile row owned by this thread (A and B)
-    const float* A = p.src_emb + (size_t)b * p.D * p.Ns;
-    const float* Bm = p.tgt_emb + (size_t)b * p.D * p.Nt;
-    const int total = num_jb * num_kb;
-    // Two register sets, loop unrolled by two: the rows of stage it+1 are requested BEFORE stage it is
-    // converted and stored, so their L2 latency overlaps ~300 instructions of split/STS work (and the
-    // wait for a free stage when the tensor core is the bottleneck).
-    float va[SC_BK], vb[SC_BK], wa[SC_BK], wb[SC_BK];
+    const int r = tid - SC_EPI_THREADS;
     bool ok = true;
-    auto step = [&](int it, float (&ca)[SC_BK], float (&cb)[SC_BK], float (&na)[SC_BK], float (&nb)[SC_BK]) {
-      if (it + 1 < total) {
-        const int njb = (it + 1) / num_kb, nkb = (it + 1) - njb * num_kb;
-        sc_load_row(A, p.D, p.Ns, nkb * SC_BK, i0 + r, na);
-        sc_load_row(Bm, p.D, p.Nt, nkb * SC_BK, njb * SC_BN + r, nb);
+    if (USE_TMA) {
+      // -------------------------------------------- splitters: lo = tf32(x - trunc_tf32(x)), smem -> smem
+      for (int it = 0; it < total; ++it) {
+        const int s = it % SC_STAGES;
+        const uint32_t n = (uint32_t)(it / SC_STAGES);
+        const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
+        if (!mbar_wait_bounded(&sh->tma_full[s], n & 1u)) { ok = false; break; }
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          const uint32_t hi = st + op * 2 * SC_TILE_BYTES, lo = hi + SC_TILE_BYTES;
+#pragma unroll
+          for (int q = 0; q < SC_TILE_BYTES / 16 / SC_PROD_THREADS; ++q) {
+            const uint32_t off = (uint32_t)(q * SC_PROD_THREADS + r) * 16u;
+            const uint4 x = lds128(hi + off);
+            uint4 y;
+            y.x = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(x.x & 0xffffe000u))));
+            y.y = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(x.y & 0xffffe000u))));
+            y.z = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(x.z & 0xffffe000u))));
+            y.w = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(x.w & 0xffffe000u))));
+            sts128(lo + off, y);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&sh->full[s]);
       }
-      const int s = it % SC_STAGES;
-      const uint32_t n = (uint32_t)(it / SC_STAGES);
-      unsigned char* st = tiles + s * SC_STAGE_BYTES;
-      if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; return; }
-      sc_store_row(st, st + SC_TILE_BYTES, r, ca);
-      sc_store_row(st + 2 * SC_TILE_BYTES, st + 3 * SC_TILE_BYTES, r, cb);
-      fence_proxy_async();
-      mbar_arrive(&sh->full[s]);
-    };
-    sc_load_row(A, p.D, p.Ns, 0, i0 + r, va);
-    sc_load_row(Bm, p.D, p.Nt, 0, r, vb);
-    for (int it = 0; it < total && ok; it += 2) {
-      step(it, va, vb, wa, wb);
-      if (it + 1 < total && ok) step(it + 1, wa, wb, va, vb);
+    } else {
+      // -------------------------------------------- generic producers: LDG, split, K-major swizzled STS
+      const float* A = p.src_emb + (size_t)b * p.D * p.Ns;
+      const float* Bm = p.tgt_emb + (size_t)b * p.D * p.Nt;
+      float va[SC_BK], vb[SC_BK];
+      for (int it = 0; it < total; ++it) {
+        const int jb = it / num_kb, kb = it - jb * num_kb;
+        sc_load_row(A, p.D, p.Ns, kb * SC_BK, i0 + r, va);
+        sc_load_row(Bm, p.D, p.Nt, kb * SC_BK, jb * SC_BN + r, vb);
+        const int s = it % SC_STAGES;
+        const uint32_t n = (uint32_t)(it / SC_STAGES);
+        const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
+        if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }
+        sc_store_row(st, st + SC_TILE_BYTES, r, va);
+        sc_store_row(st + 2 * SC_TILE_BYTES, st + 3 * SC_TILE_BYTES, r, vb);
+        fence_proxy_async();
+        mbar_arrive(&sh->full[s]);
+      }
     }
-    if (!ok) { sh->failed = 1; atomicCAS(p.err, 0, 2); }
-  } else {
+    if (!ok) atomicCAS(p.err, 0, 2);
+  } else if (warp == 8) {
     // ------------------------------------------------ MMA issuer
     bool ok = true;
     int it = 0;
@@ -324,15 +369,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
         if (!mbar_wait_bounded(&sh->full[s], n & 1u)) { ok = false; break; }
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(tiles + s * SC_STAGE_BYTES);
-          const uint64_t a_hi = sc_smem_desc(sa), a_lo = sc_smem_desc(sa + SC_TILE_BYTES);
-          const uint64_t b_hi = sc_smem_desc(sa + 2 * SC_TILE_BYTES), b_lo = sc_smem_desc(sa + 3 * SC_TILE_BYTES);
+          const uint32_t sa = tiles_s + s * SC_STAGE_BYTES;
+          const uint32_t lbo = USE_TMA ? 4096u : 16u, sbo = 1024u;
+          const uint32_t idesc = USE_TMA ? SC_IDESC_MN : SC_IDESC_K;
+          const uint64_t a_hi = sc_desc(sa, lbo, sbo), a_lo = sc_desc(sa + SC_TILE_BYTES, lbo, sbo);
+          const uint64_t b_hi = sc_desc(sa + 2 * SC_TILE_BYTES, lbo, sbo), b_lo = sc_desc(sa + 3 * SC_TILE_BYTES, lbo, sbo);
 #pragma unroll
           for (int k = 0; k < SC_BK / SC_UK; ++k) {
-            const uint64_t adv = (uint64_t)((k * SC_UK * 4) >> 4);   // +32 bytes along K inside the swizzle row
-            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, SC_IDESC, (kb | k) != 0);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, SC_IDESC, 1u);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, SC_IDESC, 1u);
+            // K-major: +32 bytes inside the 128 B swizzle row; MN-major: next 8-channel group (+1024 B)
+            const uint64_t adv = (uint64_t)((USE_TMA ? k * 1024 : k * SC_UK * 4) >> 4);
+            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           tc_commit(&sh->empty[s]);
           if (kb == num_kb - 1) tc_commit(&sh->acc_full[a]);
@@ -340,7 +388,27 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
         __syncwarp();
       }
     }
-    if (!ok && lane == 0) { sh->failed = 1; atomicCAS(p.err, 0, 3); }
+    if (!ok && lane == 0) atomicCAS(p.err, 0, 3);
+  } else if (USE_TMA) {
+    // ------------------------------------------------ TMA issuer: 8 boxes of [32 d x 32 n] per stage
+    bool ok = true;
+    for (int it = 0; it < total; ++it) {
+      const int jb = it / num_kb, kb = it - jb * num_kb;
+      const int s = it % SC_STAGES;
+      const uint32_t n = (uint32_t)(it / SC_STAGES);
+      if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }
+      if (lane == 0) {
+        const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
+        mbar_arrive_expect_tx(&sh->tma_full[s], 2 * SC_TILE_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tma_load_3d(st + q * 4096, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+          tma_load_3d(st + 2 * SC_TILE_BYTES + q * 4096, &tmap_b, jb * SC_BN + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+        }
+      }
+      __syncwarp();
+    }
+    if (!ok && lane == 0) atomicCAS(p.err, 0, 4);
   }
 
   tc_fence_before();
@@ -354,9 +422,43 @@ __global__ void __launch_bounds__(SC_THREADS, 1) softcorr_kernel(const SoftCorrP
 
 size_t softcorr_smem_bytes() { return (size_t)SC_STAGES * SC_STAGE_BYTES + sizeof(SoftCorrShared) + 1024; }
 
+// ---- host: tensor maps ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// emb [B, D, N] fp32 as a 3-D tensor (n fastest); boxes of 32 n x 32 d, 128B-swizzled; OOB -> 0
+static bool make_emb_tmap(CUtensorMap* m, const float* emb, int B, int D, int N) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * (cuuint64_t)D * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)emb, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace l3d
 
 using namespace l3d;
+
+static int g_softcorr_force_generic = 0;
 
 static int softcorr_launch(const float* src_emb, const float* tgt_emb, const float* tgt_xyz, int B, int D,
                            int Ns, int Nt, float* src_corr, float* dbg_scores, void* stream) {
@@ -368,7 +470,9 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
   static bool attr_set = false;
   const size_t smem = softcorr_smem_bytes();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(softcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -381,7 +485,17 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
   if (e != cudaSuccess) return (int)e;
   p.err = (int*)errp;
   dim3 grid((Ns + SC_BM - 1) / SC_BM, B);
-  softcorr_kernel<<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p);
+
+  // TMA needs 16-byte global strides and bases
+  bool tma = !g_softcorr_force_generic && (Ns % 4 == 0) && (Nt % 4 == 0) &&
+             (((uintptr_t)src_emb | (uintptr_t)tgt_emb) & 15) == 0;
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
+  if (tma) tma = make_emb_tmap(&ma, src_emb, B, D, Ns) && make_emb_tmap(&mb, tgt_emb, B, D, Nt);
+  if (tma)
+    softcorr_kernel<true><<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p, ma, mb);
+  else
+    softcorr_kernel<false><<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p, ma, mb);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
@@ -400,8 +514,11 @@ extern "C" int l3d_debug_soft_correspondence_scores(const float* src_emb, const 
   return softcorr_launch(src_emb, tgt_emb, tgt_xyz, B, D, Ns, Nt, src_corr, scores_dev, stream);
 }
 
+// Testing hook: nonzero forces the generic (LDG producer) operand pipeline even for TMA-eligible shapes.
+extern "C" void l3d_debug_soft_correspondence_force_generic(int on) { g_softcorr_force_generic = on; }
+
 // Synchronises the device and returns the pipeline error word of l3d_soft_correspondence
-// (0 = ok; 1/2/3 = an epilogue / producer / MMA-issuer wait ran out).  Test and debug aid.
+// (0 = ok; 1/2/3/4 = an epilogue / producer / MMA-issuer / TMA-issuer wait ran out).  Test and debug aid.
 extern "C" int l3d_soft_correspondence_status(void) {
   int v = 0;
   cudaError_t e = cudaDeviceSynchronize();

@@ -47,6 +47,10 @@ def report(name, src_emb, tgt_emb, tgt):
 
 
 torch.manual_seed(0)
+MODE = "tma"
+if len(sys.argv) > 1 and sys.argv[1] == "generic":
+    MODE = "generic"; lib.l3d_debug_soft_correspondence_force_generic(1)
+print("operand pipeline:", MODE)
 # E1: one tile, one K block
 B, D, N = 1, 32, 128
 a = torch.randn(B, D, N, device=DEV); b = torch.randn(B, D, N, device=DEV); t = torch.rand(B, 3, N, device=DEV)
@@ -72,7 +76,7 @@ if es > 1e-3:
     sys.exit(1)
 
 # larger shapes
-for (B, D, Ns, Nt) in [(1, 64, 128, 256), (2, 96, 200, 333), (2, 512, 1024, 1024)]:
+for (B, D, Ns, Nt) in [(1, 64, 128, 256), (2, 96, 200, 333), (3, 80, 1000, 516), (2, 512, 1024, 1024)]:
     a = torch.randn(B, D, Ns, device=DEV); b = torch.randn(B, D, Nt, device=DEV); t = torch.rand(B, 3, Nt, device=DEV)
     report("rand B%d D%d Ns%d Nt%d" % (B, D, Ns, Nt), a, b, t)
 # peaky softmax (trained-like embeddings)
