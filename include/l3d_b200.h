@@ -290,6 +290,9 @@ int l3d_soft_correspondence_status(void);
 /* Testing hook: nonzero forces the generic (LDG producer, any shape) operand pipeline even when the
  * shape is eligible for the TMA pipeline (Ns, Nt multiples of 4, 16-byte aligned embeddings). */
 void l3d_debug_soft_correspondence_force_generic(int on);
+/* Debug aid: shared-memory image (4 x 4096 floats: A_hi, A_lo, B_hi, B_lo) of the first pipeline stage of
+ * CTA (0,0) in the last l3d_debug_soft_correspondence_scores launch on the TMA path -> host_out. */
+int l3d_debug_soft_correspondence_tiles(float* host_out);
 /* Debug variant of l3d_soft_correspondence that also dumps the raw score accumulators
  * (src_emb^T . tgt_emb, before the 1/sqrt(D) scaling) to scores_dev [B,Ns,Nt]; used by the GEMM parity test. */
 int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* tgt_emb_dev,

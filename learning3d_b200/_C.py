@@ -55,6 +55,7 @@ _SIGNATURES = {
     "l3d_soft_correspondence": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_soft_correspondence_status": [],
     "l3d_debug_soft_correspondence_force_generic": [_I],
+    "l3d_debug_soft_correspondence_tiles": [_P],
     "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -71,6 +71,7 @@ struct SoftCorrShared {
 };
 
 __device__ int g_softcorr_error = 0;
+__device__ float g_softcorr_dbg_tiles[4 * SC_TILE_BYTES / 4];   // stage-0 operand tiles of CTA (0,0), debug entry only
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -331,6 +332,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             sts128(lo + off, y);
           }
         }
+        if (p.dbg_scores && it == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+          for (int w = r; w < SC_STAGE_BYTES / 4; w += SC_PROD_THREADS)
+            g_softcorr_dbg_tiles[w] = *reinterpret_cast<const float*>(tiles + s * SC_STAGE_BYTES + w * 4);
+        }
         fence_proxy_async();
         mbar_arrive(&sh->full[s]);
       }
@@ -512,6 +517,14 @@ extern "C" int l3d_debug_soft_correspondence_scores(const float* src_emb, const 
                                                     float* src_corr, float* scores_dev, void* stream) {
   if (!scores_dev) return L3D_ERR_INVALID;
   return softcorr_launch(src_emb, tgt_emb, tgt_xyz, B, D, Ns, Nt, src_corr, scores_dev, stream);
+}
+
+// Debug aid: copies the stage-0 operand tiles (A_hi, A_lo, B_hi, B_lo; 4 x 4096 floats, shared-memory image)
+// that CTA (0,0) of the last l3d_debug_soft_correspondence_scores launch saw on the TMA path.
+extern "C" int l3d_debug_soft_correspondence_tiles(float* host_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(host_out, g_softcorr_dbg_tiles, sizeof(float) * SC_STAGE_BYTES / 4);
 }
 
 // Testing hook: nonzero forces the generic (LDG producer) operand pipeline even for TMA-eligible shapes.

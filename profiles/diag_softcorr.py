@@ -59,6 +59,20 @@ if st != 0 or rc != 0:
     print("pipeline failure; stop"); sys.exit(2)
 if es > 1e-3:
     print("S[0,:4,:8] =", sc[0, :4, :8].cpu().numpy()); print("ref        =", s_ref[0, :4, :8].float().cpu().numpy())
+    if MODE == "tma":
+        import numpy as np, ctypes
+        buf = np.zeros(4 * 4096, dtype=np.float32)
+        print("tiles rc", lib.l3d_debug_soft_correspondence_tiles(buf.ctypes.data_as(ctypes.c_void_p)))
+        names = ["A_hi", "A_lo", "B_hi", "B_lo"]
+        an = a[0].cpu().numpy()   # [D, N]
+        for t_i, nm in enumerate(names):
+            tl = buf[t_i * 4096:(t_i + 1) * 4096]
+            print(nm, "nonzero", int((tl != 0).sum()), "absmax %.3e" % float(np.abs(tl).max()), "first8", tl[:8])
+        # where did a[d=0, n=0..7] land?  expected (unswizzled) atom 0, row d=0, floats 0..7
+        tl = buf[:4096]
+        for (d, n) in [(0, 0), (0, 4), (1, 0), (1, 4), (8, 0), (0, 32), (0, 33)]:
+            pos = np.nonzero(tl == an[d, n])[0]
+            print("a[d=%d,n=%d]=%.6f found at float offsets %s" % (d, n, an[d, n], pos[:4]))
     # E2: one-hot channels: src_emb[d,i] = (d == i%32), tgt_emb[d,j] = (d == j%32)*(1+j)
     ii = torch.arange(N, device=DEV)
     a2 = torch.zeros(B, D, N, device=DEV); a2[0, ii % D, ii] = 1.0
