@@ -161,13 +161,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 //   K-major  (generic path): rows of 32 fp32 (128 B), 8-row groups 1024 B apart (SBO).
 //   MN-major (TMA path): 128 B of n per channel row, 8-channel groups 1024 B apart (SBO), the next
 //            32 points 4096 B further (LBO).
-__device__ __forceinline__ uint64_t sc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t sc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address            bits [0,14)
   d |= (uint64_t)(lbo_bytes >> 4) << 16;           // leading byte offset      bits [16,30)
   d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset       bits [32,46)
   d |= (uint64_t)1 << 46;                          // descriptor version 1     bits [46,48)
-  d |= (uint64_t)2 << 61;                          // layout = SWIZZLE_128B    bits [61,64)
+  d |= (uint64_t)layout_type << 61;                // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = 128
@@ -375,10 +376,12 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = tiles_s + s * SC_STAGE_BYTES;
-          const uint32_t lbo = USE_TMA ? 4096u : 16u, sbo = 1024u;
+          // MN-major tf32 operands exist only in the 32-byte-atom flavour of the 128 B swizzle
+          // (UMMA layout 1 = TMA SWIZZLE_128B_ATOM_32B): 4-channel groups 512 B apart.
+          const uint32_t lbo = USE_TMA ? 4096u : 16u, sbo = USE_TMA ? 512u : 1024u, lay = USE_TMA ? 1u : 2u;
           const uint32_t idesc = USE_TMA ? SC_IDESC_MN : SC_IDESC_K;
-          const uint64_t a_hi = sc_desc(sa, lbo, sbo), a_lo = sc_desc(sa + SC_TILE_BYTES, lbo, sbo);
-          const uint64_t b_hi = sc_desc(sa + 2 * SC_TILE_BYTES, lbo, sbo), b_lo = sc_desc(sa + 3 * SC_TILE_BYTES, lbo, sbo);
+          const uint64_t a_hi = sc_desc(sa, lbo, sbo, lay), a_lo = sc_desc(sa + SC_TILE_BYTES, lbo, sbo, lay);
+          const uint64_t b_hi = sc_desc(sa + 2 * SC_TILE_BYTES, lbo, sbo, lay), b_lo = sc_desc(sa + 3 * SC_TILE_BYTES, lbo, sbo, lay);
 #pragma unroll
           for (int k = 0; k < SC_BK / SC_UK; ++k) {
             // K-major: +32 bytes inside the 128 B swizzle row; MN-major: next 8-channel group (+1024 B)
@@ -455,7 +458,7 @@ static bool make_emb_tmap(CUtensorMap* m, const float* emb, int B, int D, int N)
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)emb, dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
