@@ -1,8 +1,10 @@
 """Drop-in for learning3d/utils/svd.py:5-59 (DCP's SVD head).
 
 Same constructor, state_dict key (`reflect`) and forward contract.  The soft-correspondence front
-half (score GEMM, softmax, src_corr GEMM: dense contractions) stays on torch /
-cuBLAS; the tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
+half (score GEMM, softmax, src_corr GEMM: svd.py:23-28) is ONE fused
+tcgen05 kernel (l3d_soft_correspondence: 3xTF32 score tiles in TMEM, online softmax, never writes the
+[B,N,N] score matrix) whenever no gradient is required; with autograd it stays on the reference's torch
+ops.  The tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
 branch (svd.py:38-51) and t — is ONE launch of l3d_svd_head_tail for the whole batch, and its backward
 (the reference trains through torch.svd's autograd) ONE launch of l3d_svd_head_tail_backward.
 """
@@ -41,6 +43,28 @@ class _SVDTail(torch.autograd.Function):
         return g_src, g_corr
 
 
+def soft_correspondence(src_embedding, tgt_embedding, tgt):
+    """svd.py:23-28 fused, forward only: softmax(src_emb^T tgt_emb / sqrt(d_k)) applied to tgt.
+
+    src_embedding [B,D,Ns], tgt_embedding [B,D,Nt], tgt [B,3,Nt] (CUDA fp32) -> src_corr [B,3,Ns].
+    One tcgen05 kernel (3xTF32 score tiles in TMEM + online softmax); the [B,Ns,Nt] score matrix of the
+    reference is never written.  No autograd: SVDHead.forward uses it when no gradient is required.
+    """
+    src_embedding = _C.require_cuda(src_embedding, "src_embedding")
+    tgt_embedding = _C.require_cuda(tgt_embedding, "tgt_embedding")
+    tgt = _C.require_cuda(tgt, "tgt")
+    B, D, Ns = src_embedding.shape
+    Nt = tgt_embedding.shape[2]
+    if tgt_embedding.shape[0] != B or tgt_embedding.shape[1] != D or tuple(tgt.shape) != (B, 3, Nt):
+        raise ValueError("soft_correspondence: inconsistent shapes %s %s %s" % (
+            tuple(src_embedding.shape), tuple(tgt_embedding.shape), tuple(tgt.shape)))
+    out = torch.empty((B, 3, Ns), dtype=torch.float32, device=src_embedding.device)
+    with _C.on_device(src_embedding.device):
+        _C.check(_C.lib().l3d_soft_correspondence(_C.ptr(src_embedding), _C.ptr(tgt_embedding), _C.ptr(tgt),
+                                                  B, D, Ns, Nt, _C.ptr(out), _C.stream()), "soft_correspondence")
+    return out
+
+
 def svd_head_tail(src, src_corr):
     """src, src_corr [B,3,N] (CUDA fp32) -> R [B,3,3], t [B,3]; differentiable."""
     return _SVDTail.apply(_C.require_cuda(src, "src"), _C.require_cuda(src_corr, "src_corr"))
@@ -59,8 +83,15 @@ class SVDHead(nn.Module):
         if self.input_shape == "bnc":
             src = src.permute(0, 2, 1)
             tgt = tgt.permute(0, 2, 1)
-        d_k = src_embedding.size(1)
-        scores = torch.matmul(src_embedding.transpose(2, 1).contiguous(), tgt_embedding) / math.sqrt(d_k)
-        scores = torch.softmax(scores, dim=2)
-        src_corr = torch.matmul(tgt, scores.transpose(2, 1).contiguous())
+        needs_grad = torch.is_grad_enabled() and any(
+            t.requires_grad for t in (src_embedding, tgt_embedding, src, tgt))
+        if not needs_grad:
+            # inference: scores, softmax and the correspondence GEMM are one fused tcgen05 kernel
+            src_corr = soft_correspondence(src_embedding, tgt_embedding, tgt)
+        else:
+            # training: autograd needs the score matrix; same torch ops as the reference (svd.py:23-28)
+            d_k = src_embedding.size(1)
+            scores = torch.matmul(src_embedding.transpose(2, 1).contiguous(), tgt_embedding) / math.sqrt(d_k)
+            scores = torch.softmax(scores, dim=2)
+            src_corr = torch.matmul(tgt, scores.transpose(2, 1).contiguous())
         return svd_head_tail(src, src_corr)
