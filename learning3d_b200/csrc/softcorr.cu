@@ -37,17 +37,27 @@
 namespace l3d {
 
 constexpr int SC_BM = 128;                 // source points per CTA  (UMMA M)
-constexpr int SC_BN = 128;                 // target points per tile (UMMA N)
-constexpr int SC_BK = 32;                  // embedding channels per stage
 constexpr int SC_UK = 8;                   // UMMA K for kind::tf32 (32 bytes)
-constexpr int SC_STAGES = 3;
-constexpr int SC_TILE_BYTES = SC_BM * SC_BK * 4;       // 16 KB per operand tile
-constexpr int SC_STAGE_BYTES = 4 * SC_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int SC_EPI_THREADS = 128;
 constexpr int SC_PROD_THREADS = 128;
 constexpr int SC_THREADS = SC_EPI_THREADS + SC_PROD_THREADS + 64;   // + MMA warp + TMA warp
-constexpr int SC_TMEM_COLS = 2 * SC_BN;    // two fp32 accumulators
 constexpr uint32_t SC_SPIN_LIMIT = 1u << 22;
+constexpr int SC_MAX_BN = 256, SC_MAX_STAGES = 4;
+
+// Tile configuration per operand pipeline.  The kernel is shared-memory-bandwidth bound (TMA writes,
+// the splitters' read + write and the tensor core's operand reads all cross the same 128 B/clk port), so
+// the TMA path uses N = 256 MMAs: A is read once per 256 target points instead of once per 128.
+template <bool USE_TMA>
+struct SoftCorrCfg {
+  static constexpr int BN = USE_TMA ? 256 : 128;      // target points per tile (UMMA N)
+  static constexpr int BK = USE_TMA ? 16 : 32;        // embedding channels per stage
+  static constexpr int STAGES = USE_TMA ? 4 : 3;
+  static constexpr int A_TILE = SC_BM * BK * 4;       // bytes: 8 KB / 16 KB
+  static constexpr int B_TILE = BN * BK * 4;          // bytes: 16 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;   // A_hi, A_lo, B_hi, B_lo: 48 KB / 64 KB
+  static constexpr int TMEM_COLS = 2 * BN;            // two fp32 accumulators
+  static constexpr int ATOM = 32 * BK * 4;            // TMA path: bytes of one [BK d x 32 n] box
+};
 
 struct SoftCorrParams {
   const float* src_emb;   // [B, D, Ns]
@@ -61,17 +71,17 @@ struct SoftCorrParams {
 };
 
 struct SoftCorrShared {
-  float4 xyz[2][SC_BN];
-  uint64_t tma_full[SC_STAGES];   // TMA path: raw tiles landed
-  uint64_t full[SC_STAGES];       // all four operand tiles of the stage are ready for the MMA
-  uint64_t empty[SC_STAGES];      // the MMAs reading the stage have completed
+  float4 xyz[2][SC_MAX_BN];
+  uint64_t tma_full[SC_MAX_STAGES];   // TMA path: raw tiles landed
+  uint64_t full[SC_MAX_STAGES];       // all four operand tiles of the stage are ready for the MMA
+  uint64_t empty[SC_MAX_STAGES];      // the MMAs reading the stage have completed
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
 };
 
 __device__ int g_softcorr_error = 0;
-__device__ float g_softcorr_dbg_tiles[4 * SC_TILE_BYTES / 4];   // stage-0 operand tiles of CTA (0,0), debug entry only
+__device__ float g_softcorr_dbg_tiles[SoftCorrCfg<true>::STAGE / 4];   // stage-0 operand tiles of CTA (0,0), debug entry only
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -171,10 +181,13 @@ __device__ __forceinline__ uint64_t sc_desc(uint32_t saddr, uint32_t lbo_bytes, 
   d |= (uint64_t)layout_type << 61;                // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = 128
-constexpr uint32_t SC_IDESC_K = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SC_BN >> 3) << 17) |
-                                ((uint32_t)(SC_BM >> 4) << 24);
-constexpr uint32_t SC_IDESC_MN = SC_IDESC_K | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = bn;
+// mn_major sets a_major = b_major = MN
+__host__ __device__ constexpr uint32_t sc_idesc(int bn, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(SC_BM >> 4) << 24) |
+         (mn_major ? ((1u << 15) | (1u << 16)) : 0u);
+}
+constexpr int SC_GBK = SoftCorrCfg<false>::BK;   // generic pipeline: channels per stage (one 128 B swizzle row)
 
 // byte offset of (row r, 16-byte chunk c) inside a K-major [128 x 32 fp32] swizzled tile
 __device__ __forceinline__ uint32_t sc_swz(int r, int c) {
@@ -183,15 +196,15 @@ __device__ __forceinline__ uint32_t sc_swz(int r, int c) {
 
 // ---- generic producer helpers -------------------------------------------------------------------
 __device__ __forceinline__ void sc_load_row(const float* __restrict__ base, int D, int N, int d0,
-                                            int n, float (&v)[SC_BK]) {
+                                            int n, float (&v)[SC_GBK]) {
   const bool nv = n < N;
   const float* p = base + (size_t)d0 * N + (nv ? n : 0);
 #pragma unroll
-  for (int dd = 0; dd < SC_BK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + (size_t)dd * N) : 0.f;
+  for (int dd = 0; dd < SC_GBK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + (size_t)dd * N) : 0.f;
 }
-__device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile, int r, const float (&v)[SC_BK]) {
+__device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile, int r, const float (&v)[SC_GBK]) {
 #pragma unroll
-  for (int c = 0; c < SC_BK / 4; ++c) {
+  for (int c = 0; c < SC_GBK / 4; ++c) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -209,6 +222,9 @@ template <bool USE_TMA>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap_a,
                 const __grid_constant__ CUtensorMap tmap_b) {
+  using Cfg = SoftCorrCfg<USE_TMA>;
+  constexpr int SC_BN = Cfg::BN, SC_BK = Cfg::BK, SC_STAGES = Cfg::STAGES, SC_STAGE_BYTES = Cfg::STAGE;
+  constexpr int A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE, SC_TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ unsigned char sc_raw[];
   // 1024-byte alignment: the swizzle XOR is applied to absolute shared addresses
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
@@ -253,14 +269,15 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     for (int jb = 0; jb < num_jb; ++jb) {
       const int a = jb & 1;
       const int j0 = jb * SC_BN;
-      {
-        const int j = j0 + tid;
+#pragma unroll
+      for (int jj = tid; jj < SC_BN; jj += SC_EPI_THREADS) {
+        const int j = j0 + jj;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < p.Nt) {
           const float* t = p.tgt_xyz + (size_t)b * 3 * p.Nt + j;
           q = make_float4(__ldg(t), __ldg(t + p.Nt), __ldg(t + 2 * (size_t)p.Nt), 0.f);
         }
-        sh->xyz[a][tid] = q;
+        sh->xyz[a][jj] = q;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (!mbar_wait_bounded(&sh->acc_full[a], (uint32_t)((jb >> 1) & 1))) { ok = false; break; }
@@ -320,9 +337,9 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         if (!mbar_wait_bounded(&sh->tma_full[s], n & 1u)) { ok = false; break; }
 #pragma unroll
         for (int op = 0; op < 2; ++op) {
-          const uint32_t hi = st + op * 2 * SC_TILE_BYTES, lo = hi + SC_TILE_BYTES;
+          const uint32_t hi = st + (op ? 2 * A_TILE : 0), lo = hi + (op ? B_TILE : A_TILE);
 #pragma unroll
-          for (int q = 0; q < SC_TILE_BYTES / 16 / SC_PROD_THREADS; ++q) {
+          for (int q = 0; q < (op ? B_TILE : A_TILE) / 16 / SC_PROD_THREADS; ++q) {
             const uint32_t off = (uint32_t)(q * SC_PROD_THREADS + r) * 16u;
             const uint4 x = lds128(hi + off);
             uint4 y;
@@ -344,7 +361,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       // -------------------------------------------- generic producers: LDG, split, K-major swizzled STS
       const float* A = p.src_emb + (size_t)b * p.D * p.Ns;
       const float* Bm = p.tgt_emb + (size_t)b * p.D * p.Nt;
-      float va[SC_BK], vb[SC_BK];
+      float va[SC_GBK], vb[SC_GBK];
       for (int it = 0; it < total; ++it) {
         const int jb = it / num_kb, kb = it - jb * num_kb;
         sc_load_row(A, p.D, p.Ns, kb * SC_BK, i0 + r, va);
@@ -353,8 +370,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         const uint32_t n = (uint32_t)(it / SC_STAGES);
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
         if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }
-        sc_store_row(st, st + SC_TILE_BYTES, r, va);
-        sc_store_row(st + 2 * SC_TILE_BYTES, st + 3 * SC_TILE_BYTES, r, vb);
+        sc_store_row(st, st + A_TILE, r, va);
+        sc_store_row(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, r, vb);
         fence_proxy_async();
         mbar_arrive(&sh->full[s]);
       }
@@ -378,10 +395,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
           const uint32_t sa = tiles_s + s * SC_STAGE_BYTES;
           // MN-major tf32 operands exist only in the 32-byte-atom flavour of the 128 B swizzle
           // (UMMA layout 1 = TMA SWIZZLE_128B_ATOM_32B): 4-channel groups 512 B apart.
-          const uint32_t lbo = USE_TMA ? 4096u : 16u, sbo = USE_TMA ? 512u : 1024u, lay = USE_TMA ? 1u : 2u;
-          const uint32_t idesc = USE_TMA ? SC_IDESC_MN : SC_IDESC_K;
-          const uint64_t a_hi = sc_desc(sa, lbo, sbo, lay), a_lo = sc_desc(sa + SC_TILE_BYTES, lbo, sbo, lay);
-          const uint64_t b_hi = sc_desc(sa + 2 * SC_TILE_BYTES, lbo, sbo, lay), b_lo = sc_desc(sa + 3 * SC_TILE_BYTES, lbo, sbo, lay);
+          const uint32_t lbo = USE_TMA ? (uint32_t)Cfg::ATOM : 16u, sbo = USE_TMA ? 512u : 1024u, lay = USE_TMA ? 1u : 2u;
+          constexpr uint32_t idesc = sc_idesc(SC_BN, USE_TMA);
+          const uint64_t a_hi = sc_desc(sa, lbo, sbo, lay), a_lo = sc_desc(sa + A_TILE, lbo, sbo, lay);
+          const uint64_t b_hi = sc_desc(sa + 2 * A_TILE, lbo, sbo, lay), b_lo = sc_desc(sa + 2 * A_TILE + B_TILE, lbo, sbo, lay);
 #pragma unroll
           for (int k = 0; k < SC_BK / SC_UK; ++k) {
             // K-major: +32 bytes inside the 128 B swizzle row; MN-major: next 8-channel group (+1024 B)
@@ -398,7 +415,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     }
     if (!ok && lane == 0) atomicCAS(p.err, 0, 3);
   } else if (USE_TMA) {
-    // ------------------------------------------------ TMA issuer: 8 boxes of [32 d x 32 n] per stage
+    // ------------------------------------------------ TMA issuer: 4 + 8 boxes of [16 d x 32 n] per stage
     bool ok = true;
     for (int it = 0; it < total; ++it) {
       const int jb = it / num_kb, kb = it - jb * num_kb;
@@ -407,12 +424,13 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }
       if (lane == 0) {
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
-        mbar_arrive_expect_tx(&sh->tma_full[s], 2 * SC_TILE_BYTES);
+        mbar_arrive_expect_tx(&sh->tma_full[s], A_TILE + B_TILE);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          tma_load_3d(st + q * 4096, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
-          tma_load_3d(st + 2 * SC_TILE_BYTES + q * 4096, &tmap_b, jb * SC_BN + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
-        }
+        for (int q = 0; q < SC_BM / 32; ++q)
+          tma_load_3d(st + q * Cfg::ATOM, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+#pragma unroll
+        for (int q = 0; q < SC_BN / 32; ++q)
+          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, jb * SC_BN + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
       }
       __syncwarp();
     }
@@ -428,7 +446,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
   }
 }
 
-size_t softcorr_smem_bytes() { return (size_t)SC_STAGES * SC_STAGE_BYTES + sizeof(SoftCorrShared) + 1024; }
+template <bool USE_TMA>
+size_t softcorr_smem_bytes() {
+  return (size_t)SoftCorrCfg<USE_TMA>::STAGES * SoftCorrCfg<USE_TMA>::STAGE + sizeof(SoftCorrShared) + 1024;
+}
 
 // ---- host: tensor maps ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -455,7 +476,7 @@ static bool make_emb_tmap(CUtensorMap* m, const float* emb, int B, int D, int N)
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)D, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * (cuuint64_t)D * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {32, (cuuint32_t)SoftCorrCfg<true>::BK, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)emb, dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -476,11 +497,11 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
   if (Nt == 0 || D == 0) return L3D_ERR_INVALID;      // softmax over an empty row is undefined
   if (B > 65535) return L3D_ERR_UNSUPPORTED;
   static bool attr_set = false;
-  const size_t smem = softcorr_smem_bytes();
+  const size_t smem_t = softcorr_smem_bytes<true>(), smem_g = softcorr_smem_bytes<false>();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(softcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(softcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -501,9 +522,9 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
   memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
   if (tma) tma = make_emb_tmap(&ma, src_emb, B, D, Ns) && make_emb_tmap(&mb, tgt_emb, B, D, Nt);
   if (tma)
-    softcorr_kernel<true><<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p, ma, mb);
+    softcorr_kernel<true><<<grid, SC_THREADS, smem_t, (cudaStream_t)stream>>>(p, ma, mb);
   else
-    softcorr_kernel<false><<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p, ma, mb);
+    softcorr_kernel<false><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
@@ -527,7 +548,7 @@ extern "C" int l3d_debug_soft_correspondence_scores(const float* src_emb, const 
 extern "C" int l3d_debug_soft_correspondence_tiles(float* host_out) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaMemcpyFromSymbol(host_out, g_softcorr_dbg_tiles, sizeof(float) * SC_STAGE_BYTES / 4);
+  return (int)cudaMemcpyFromSymbol(host_out, g_softcorr_dbg_tiles, sizeof(float) * SoftCorrCfg<true>::STAGE / 4);
 }
 
 // Testing hook: nonzero forces the generic (LDG producer) operand pipeline even for TMA-eligible shapes.

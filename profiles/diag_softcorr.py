@@ -61,15 +61,16 @@ if es > 1e-3:
     print("S[0,:4,:8] =", sc[0, :4, :8].cpu().numpy()); print("ref        =", s_ref[0, :4, :8].float().cpu().numpy())
     if MODE == "tma":
         import numpy as np, ctypes
-        buf = np.zeros(4 * 4096, dtype=np.float32)
+        buf = np.zeros(12288, dtype=np.float32)
         print("tiles rc", lib.l3d_debug_soft_correspondence_tiles(buf.ctypes.data_as(ctypes.c_void_p)))
         names = ["A_hi", "A_lo", "B_hi", "B_lo"]
         an = a[0].cpu().numpy()   # [D, N]
+        offs = [0, 2048, 4096, 8192, 12288]
         for t_i, nm in enumerate(names):
-            tl = buf[t_i * 4096:(t_i + 1) * 4096]
+            tl = buf[offs[t_i]:offs[t_i + 1]]
             print(nm, "nonzero", int((tl != 0).sum()), "absmax %.3e" % float(np.abs(tl).max()), "first8", tl[:8])
         # where did a[d=0, n=0..7] land?  expected (unswizzled) atom 0, row d=0, floats 0..7
-        tl = buf[:4096]
+        tl = buf[:2048]
         for (d, n) in [(0, 0), (0, 4), (1, 0), (1, 4), (8, 0), (0, 32), (0, 33)]:
             pos = np.nonzero(tl == an[d, n])[0]
             print("a[d=%d,n=%d]=%.6f found at float offsets %s" % (d, n, an[d, n], pos[:4]))
