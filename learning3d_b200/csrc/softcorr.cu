@@ -4,8 +4,8 @@
 //     scores   = softmax(src_emb^T . tgt_emb / sqrt(d_k), dim=2)      [B, Ns, Nt]   (134 MB at C3)
 //     src_corr = tgt . scores^T                                        [B, 3, Ns]
 // without ever writing the score matrix: one CTA owns 128 source points, walks the target points
-// in blocks of 128, and keeps a running (max, sum, sum*xyz) per source point — the flash-attention
-// recurrence with a 3-wide V.
+// in tiles of 256 (TMA pipeline) / 128 (generic), and keeps a running (max, sum, sum*xyz) per source
+// point — the flash-attention recurrence with a 3-wide V.
 //
 // Arithmetic: the score GEMM runs on the 5th-gen tensor cores as 3xTF32 — every fp32 operand x is
 // split into hi + lo,  a.b ~= hi.hi + hi.lo + lo.hi  accumulated in fp32 in TMEM: relative error
@@ -15,16 +15,17 @@
 // Two operand pipelines, one epilogue / MMA structure:
 //   TMA path (Ns, Nt multiples of 4, 16-byte aligned bases — every shape the models produce):
 //     the embeddings are [d, n]-major in HBM, which IS an MN-major UMMA operand: 3-D tensor-map TMA
-//     drops [32 d x 32 n] boxes 128B-swizzled straight into shared memory and the tensor core reads
-//     them as the hi operand (the hardware ignores the low 13 mantissa bits); four "splitter" warps
-//     only derive the lo tiles (x - trunc(x), tf32-rounded) shared-to-shared.  No thread touches
-//     global memory for the GEMM operands.
+//     drops [16 d x 32 n] boxes (SWIZZLE_128B_ATOM_32B = UMMA layout 1, the only swizzle MN-major tf32
+//     operands exist in) straight into shared memory and the tensor core reads them as the hi operand
+//     (the hardware ignores the low 13 mantissa bits); four "splitter" warps only derive the lo tiles
+//     (x - trunc(x), tf32-rounded) shared-to-shared.  No thread touches global memory for the GEMM
+//     operands.  N = 256 MMAs: the kernel is shared-memory-bandwidth bound.
 //   generic path (any shape): four producer warps load rows with LDG, split, and store K-major
 //     swizzled tiles themselves.
-//   warps 0-3  epilogue: tcgen05.ld the 128x128 score tile (lane = source point), online softmax,
+//   warps 0-3  epilogue: tcgen05.ld the 128 x BN score tile (lane = source point), online softmax,
 //              xyz accumulation; two accumulators in TMEM so it overlaps the next tile's MMAs
 //   warps 4-7  splitters / producers
-//   warp  8    one thread issues tcgen05.mma (M128 N128 K8, kind::tf32) and tcgen05.commit
+//   warp  8    one thread issues tcgen05.mma (M128 N256|128 K8, kind::tf32) and tcgen05.commit
 //   warp  9    one thread issues the TMA loads (TMA path)
 // Every mbarrier wait is bounded: a protocol bug surfaces as an error code, never as a hung GPU.
 #include "common.cuh"

@@ -44,6 +44,19 @@ def emd_forward(xyz1, xyz2):
     return matchcost(xyz1, xyz2, match), match
 
 
+def soft_correspondence(src_emb, tgt_emb, tgt):
+    """utils/svd.py:23-28 restated with numpy in fp64 (checker for the fused tcgen05 kernel):
+    src_emb [B,D,Ns], tgt_emb [B,D,Nt], tgt [B,3,Nt] -> src_corr [B,3,Ns] (returned as fp64).
+    Pinned against the real reference's fp32 output in tests/golden/svd_head.npz (tests/test_oracle_emd_svd.py)."""
+    a = np.asarray(src_emb, np.float64)
+    b = np.asarray(tgt_emb, np.float64)
+    scores = np.matmul(a.transpose(0, 2, 1), b) / np.sqrt(a.shape[1])          # :24
+    scores = scores - scores.max(axis=2, keepdims=True)
+    p = np.exp(scores)
+    p /= p.sum(axis=2, keepdims=True)                                             # :25 softmax(dim=2)
+    return np.matmul(np.asarray(tgt, np.float64), p.transpose(0, 2, 1))           # :27
+
+
 def svd_head_tail(src, src_corr):
     """utils/svd.py:29-58 restated with numpy (LAPACK gesdd, the routine torch.svd calls on CPU):
     src, src_corr [B,3,N] fp32 -> R [B,3,3], t [B,3]."""

@@ -63,6 +63,15 @@ def test_scores_and_correspondences_vs_fp64(pipeline, B, D, Ns, Nt):
     assert (out.double() - o_ref).abs().max().item() <= 2e-5, pipeline
 
 
+def test_against_real_reference_fixture(pipeline, golden_dir):
+    """src_corr computed by the unmodified reference SVDHead on CPU (tests/golden/make_golden.py)."""
+    from learning3d_b200.utils.svd import soft_correspondence
+    g = np.load(f"{golden_dir}/svd_head.npz")
+    tgt = torch.from_numpy(np.ascontiguousarray(g["tgt"].transpose(0, 2, 1))).to(DEV)
+    out = soft_correspondence(torch.from_numpy(g["src_emb"]).to(DEV), torch.from_numpy(g["tgt_emb"]).to(DEV), tgt)
+    assert np.abs(out.cpu().numpy() - g["src_corr"]).max() <= 2e-5
+
+
 def test_peaky_softmax_and_large_scores(pipeline):
     """Trained-like embeddings: scores of a few thousand, softmax essentially one-hot."""
     g = torch.Generator(device=DEV).manual_seed(7)

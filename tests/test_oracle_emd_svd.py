@@ -45,6 +45,14 @@ def test_emd_grads_match_finite_differences_of_cost_at_fixed_match(oracle_mod):
         assert abs(fd[0] - g1[0, pt, c]) < 2e-2 * max(1.0, abs(fd[0]))
 
 
+def test_soft_correspondence_restatement_matches_reference(golden_dir):
+    """oracle.emd.soft_correspondence (fp64) vs src_corr produced by the REAL reference SVDHead (fp32, CPU)."""
+    g = np.load(f"{golden_dir}/svd_head.npz")
+    got = oe.soft_correspondence(g["src_emb"], g["tgt_emb"], g["tgt"].transpose(0, 2, 1))
+    assert got.shape == g["src_corr"].shape
+    assert np.abs(got - g["src_corr"]).max() < 2e-6
+
+
 def test_svd_head_restatement_matches_reference(oracle_mod, golden_dir):
     g = np.load(f"{golden_dir}/svd_head.npz")
     R, t = oe.svd_head_tail(g["src"].transpose(0, 2, 1), g["src_corr"])
