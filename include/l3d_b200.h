@@ -61,6 +61,18 @@ void l3d_debug_force_slow_path(int on);
 int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
                       float* val_dev, void* stream);
 
+/*
+ * knn() of utils/model_common_utils.py:3-9 for any channel count C (the dynamic feature-space graphs of
+ * PRNet's DGCNN, models/prnet.py:78-90: C = 64 / 64 / 128).  x_dev [B,C,N] -> idx_dev [B,N,k] int64.
+ * Three launches on `stream`: |x_n|^2; the Gram matrix on the tensor cores (tcgen05, 3xTF32: fp32-class
+ * accuracy, NOT bit-identical to a cuBLAS / MKL SGEMM — neither are those to each other) fused with
+ * pd = ((-|x_j|^2) + 2 x_i.x_j) - |x_i|^2 into ws_dev; top-k per row (lower index first on exact ties).
+ * ws_dev: l3d_knn_features_ws_bytes(B,C,N) bytes of device scratch (16-byte aligned), no initialisation needed.
+ */
+size_t l3d_knn_features_ws_bytes(int B, int C, int N);
+int l3d_knn_features(const float* x_dev, int B, int C, int N, int k, int64_t* idx_dev, void* ws_dev,
+                     void* stream);
+
 /* Same, HOST buffers (pinned or pageable); copies + kernel + copy back, then syncs. */
 int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, int64_t* idx_host);
 

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "l3d_debug_force_slow_path": [_I],
     "l3d_knn_expansion": [_P, _I, _I, _I, _P, _P, _P],
     "l3d_knn_expansion_host": [_P, _I, _I, _I, _P],
+    "l3d_knn_features_ws_bytes": [_I, _I, _I],
+    "l3d_knn_features": [_P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_graph_feature": [_P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_graph_feature_grad": [_P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_knn_point": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
@@ -69,6 +71,7 @@ _RESTYPE = {
     "l3d_debug_force_slow_path": None,
     "l3d_debug_soft_correspondence_force_generic": None,
     "l3d_chamfer_ws_bytes": ctypes.c_size_t,
+    "l3d_knn_features_ws_bytes": ctypes.c_size_t,
     "l3d_emd_forward_ws_bytes": ctypes.c_size_t,
     "l3d_emd_backward_ws_bytes": ctypes.c_size_t,
 }

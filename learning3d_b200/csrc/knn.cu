@@ -597,6 +597,7 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
 
 // ---- host side -----------------------------------------------------------------------
 static int g_force_slow = 0;
+int knn_force_slow_flag() { return g_force_slow; }   // knn_matrix.cu shares the testing hook
 
 static int sm_count() {
   static int n = 0;

@@ -30,9 +30,11 @@
 // Every mbarrier wait is bounded: a protocol bug surfaces as an error code, never as a hung GPU.
 #include "common.cuh"
 #include "../../include/l3d_b200.h"
+#include "knn_matrix.h"
 #include "launch_count.h"
 
 #include <cuda.h>
+#include <string.h>
 #include <math.h>
 
 namespace l3d {
@@ -66,6 +68,10 @@ struct SoftCorrParams {
   const float* tgt_xyz;   // [B, 3, Nt]
   float* out;             // [B, 3, Ns]
   float* dbg_scores;      // optional [B, Ns, Nt]: raw accumulator dump (debug entry point only)
+  // EPI_KEYS (feature-space kNN): squared norms of the source / target columns and the key matrix
+  const float* xx_a;      // [B, Ns]
+  const float* xx_b;      // [B, Nt]
+  float* keys;            // [B, Ns, Nt]   ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2
   int* err;               // device error word (0 = ok)
   int B, D, Ns, Nt;
   float c;                // log2(e) / sqrt(D)
@@ -219,7 +225,10 @@ __device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile,
   }
 }
 
-template <bool USE_TMA>
+constexpr int EPI_SOFTMAX_XYZ = 0;   // SVD head: online softmax, xyz-weighted sums  -> out [B,3,Ns]
+constexpr int EPI_KEYS = 1;          // feature-space kNN: negated expansion distances -> keys [B,Ns,Nt]
+
+template <bool USE_TMA, int EPI>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap_a,
                 const __grid_constant__ CUtensorMap tmap_b) {
@@ -266,6 +275,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     const int i = i0 + tid;
     const float c = p.c;
     float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    const float xi = (EPI == EPI_KEYS && i < p.Ns) ? __ldg(p.xx_a + (size_t)b * p.Ns + i) : 0.f;
     bool ok = true;
     for (int jb = 0; jb < num_jb; ++jb) {
       const int a = jb & 1;
@@ -275,8 +285,12 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         const int j = j0 + jj;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < p.Nt) {
-          const float* t = p.tgt_xyz + (size_t)b * 3 * p.Nt + j;
-          q = make_float4(__ldg(t), __ldg(t + p.Nt), __ldg(t + 2 * (size_t)p.Nt), 0.f);
+          if (EPI == EPI_KEYS) {
+            q.x = __ldg(p.xx_b + (size_t)b * p.Nt + j);
+          } else {
+            const float* t = p.tgt_xyz + (size_t)b * 3 * p.Nt + j;
+            q = make_float4(__ldg(t), __ldg(t + p.Nt), __ldg(t + 2 * (size_t)p.Nt), 0.f);
+          }
         }
         sh->xyz[a][jj] = q;
       }
@@ -294,6 +308,31 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             if (j0 + ch * 32 + e < p.Nt) p.dbg_scores[((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32 + e] = v[e];
         }
         if (ch * 32 >= nvalid) continue;
+        if (EPI == EPI_KEYS) {
+          // pd = ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2  (model_common_utils.py:5-7, same association as knn.cu);
+          // thread = row i: 32 consecutive floats of its key row, 16-byte stores when the row allows
+          if (i < p.Ns) {
+            const float4* xz = &sh->xyz[a][ch * 32];
+            float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32;
+            const int nv = min(32, nvalid - ch * 32);
+            if (nv == 32 && (p.Nt & 3) == 0) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                float4 o;
+                o.x = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
+                o.y = __fsub_rn(fmaf(2.0f, v[e + 1], -xz[e + 1].x), xi);
+                o.z = __fsub_rn(fmaf(2.0f, v[e + 2], -xz[e + 2].x), xi);
+                o.w = __fsub_rn(fmaf(2.0f, v[e + 3], -xz[e + 3].x), xi);
+                *reinterpret_cast<float4*>(dst + e) = o;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (e < nv) dst[e] = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
+            }
+          }
+          continue;
+        }
         if (nvalid - ch * 32 < 32) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -319,7 +358,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       mbar_arrive(&sh->acc_empty[a]);
     }
     if (!ok) atomicCAS(p.err, 0, 1);
-    if (ok && i < p.Ns) {
+    if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns) {
       const float inv = __fdividef(1.f, l);
       float* o = p.out + (size_t)b * 3 * p.Ns + i;
       o[0] = __fmul_rn(ax, inv);
@@ -490,45 +529,99 @@ using namespace l3d;
 
 static int g_softcorr_force_generic = 0;
 
+// Launches the GEMM pipeline with epilogue EPI on an already filled parameter block (src_emb, tgt_emb,
+// B, D, Ns, Nt and the epilogue's own pointers).
+template <int EPI>
+static int sc_launch(SoftCorrParams p, void* stream) {
+  if (p.B > 65535) return L3D_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  const size_t smem_t = softcorr_smem_bytes<true>(), smem_g = softcorr_smem_bytes<false>();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(softcorr_kernel<false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  p.c = (float)(1.4426950408889634 / sqrt((double)p.D));
+  void* errp = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&errp, g_softcorr_error);
+  if (e != cudaSuccess) return (int)e;
+  p.err = (int*)errp;
+  dim3 grid((p.Ns + SC_BM - 1) / SC_BM, p.B);
+
+  // TMA needs 16-byte global strides and bases
+  bool tma = !g_softcorr_force_generic && (p.Ns % 4 == 0) && (p.Nt % 4 == 0) &&
+             (((uintptr_t)p.src_emb | (uintptr_t)p.tgt_emb) & 15) == 0;
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
+  if (tma) tma = make_emb_tmap(&ma, p.src_emb, p.B, p.D, p.Ns) && make_emb_tmap(&mb, p.tgt_emb, p.B, p.D, p.Nt);
+  if (tma)
+    softcorr_kernel<true, EPI><<<grid, SC_THREADS, smem_t, (cudaStream_t)stream>>>(p, ma, mb);
+  else
+    softcorr_kernel<false, EPI><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
 static int softcorr_launch(const float* src_emb, const float* tgt_emb, const float* tgt_xyz, int B, int D,
                            int Ns, int Nt, float* src_corr, float* dbg_scores, void* stream) {
   if (B < 0 || D < 0 || Ns < 0 || Nt < 0) return L3D_ERR_INVALID;
   if (B == 0 || Ns == 0) return L3D_OK;
   if (!src_emb || !tgt_emb || !tgt_xyz || !src_corr) return L3D_ERR_INVALID;
   if (Nt == 0 || D == 0) return L3D_ERR_INVALID;      // softmax over an empty row is undefined
-  if (B > 65535) return L3D_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  const size_t smem_t = softcorr_smem_bytes<true>(), smem_g = softcorr_smem_bytes<false>();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(softcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
   p.src_emb = src_emb; p.tgt_emb = tgt_emb; p.tgt_xyz = tgt_xyz; p.out = src_corr; p.dbg_scores = dbg_scores;
   p.B = B; p.D = D; p.Ns = Ns; p.Nt = Nt;
-  p.c = (float)(1.4426950408889634 / sqrt((double)D));
-  void* errp = nullptr;
-  cudaError_t e = cudaGetSymbolAddress(&errp, g_softcorr_error);
-  if (e != cudaSuccess) return (int)e;
-  p.err = (int*)errp;
-  dim3 grid((Ns + SC_BM - 1) / SC_BM, B);
+  return sc_launch<EPI_SOFTMAX_XYZ>(p, stream);
+}
 
-  // TMA needs 16-byte global strides and bases
-  bool tma = !g_softcorr_force_generic && (Ns % 4 == 0) && (Nt % 4 == 0) &&
-             (((uintptr_t)src_emb | (uintptr_t)tgt_emb) & 15) == 0;
-  CUtensorMap ma, mb;
-  memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
-  if (tma) tma = make_emb_tmap(&ma, src_emb, B, D, Ns) && make_emb_tmap(&mb, tgt_emb, B, D, Nt);
-  if (tma)
-    softcorr_kernel<true><<<grid, SC_THREADS, smem_t, (cudaStream_t)stream>>>(p, ma, mb);
-  else
-    softcorr_kernel<false><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);
+// ---- feature-space kNN: knn() of utils/model_common_utils.py:3-9 for C != 3 -----------------------------
+// xx[b,n] = sum_c x[b,c,n]^2, accumulated in channel order (torch.sum(x**2, dim=1), :6)
+__global__ void sqnorm_kernel(const float* __restrict__ x, int B, int C, int N, float* __restrict__ xx) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * N) return;
+  const int b = (int)(t / N), n = (int)(t - (long)b * N);
+  const float* p = x + (size_t)b * C * N + n;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(p + (size_t)c * N);
+    acc = __fadd_rn(acc, __fmul_rn(v, v));
+  }
+  xx[t] = acc;
+}
+
+static size_t knn_features_keys_bytes(int B, int N) {
+  return (((size_t)B * N * N * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+extern "C" size_t l3d_knn_features_ws_bytes(int B, int C, int N) {
+  (void)C;
+  if (B <= 0 || N <= 0) return 0;
+  return knn_features_keys_bytes(B, N) + (size_t)B * N * sizeof(float);
+}
+
+extern "C" int l3d_knn_features(const float* x_dev, int B, int C, int N, int k, int64_t* idx_dev, void* ws_dev,
+                                void* stream) {
+  if (B < 0 || C < 1 || N < 0 || k < 1) return L3D_ERR_INVALID;
+  if (B == 0 || N == 0) return L3D_OK;
+  if (!x_dev || !idx_dev || !ws_dev || k > N) return L3D_ERR_INVALID;
+  if (((uintptr_t)ws_dev & 15) != 0) return L3D_ERR_INVALID;
+  float* keys = reinterpret_cast<float*>(ws_dev);
+  float* xx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws_dev) + knn_features_keys_bytes(B, N));
+  const long rows = (long)B * N;
+  sqnorm_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, B, C, N, xx);
   count_launch();
   L3D_LAUNCH_CHECK();
-  return L3D_OK;
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = x_dev; p.tgt_emb = x_dev; p.xx_a = xx; p.xx_b = xx; p.keys = keys;
+  p.B = B; p.D = C; p.Ns = N; p.Nt = N;
+  int rc = sc_launch<EPI_KEYS>(p, stream);
+  if (rc != L3D_OK) return rc;
+  return knn_select_from_matrix(keys, rows, N, k, reinterpret_cast<long long*>(idx_dev), (cudaStream_t)stream);
 }
 
 extern "C" int l3d_soft_correspondence(const float* src_emb, const float* tgt_emb, const float* tgt_xyz,

@@ -20,14 +20,18 @@ def knn(x, k, add_one_to_k=False):
     if x.dim() != 3:
         raise ValueError("knn expects x of shape [B, C, N], got %s" % (tuple(x.shape),))
     B, C, N = x.shape
-    if C != 3:
-        raise NotImplementedError(
-            "learning3d_b200.knn: C=%d — only the xyz graph (C == 3) is on the built hot path; "
-            "feature-space kNN is a 'next' row (SURVEY.md §8f)" % C)
     if k > N:
         # same failure class as torch.topk in the reference
         raise RuntimeError("selected index k out of range")
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    if C != 3:
+        # feature-space graph (PRNet's dynamic DGCNN, models/prnet.py:78-90): Gram matrix on the tensor
+        # cores (tcgen05 3xTF32) fused with the expansion keys, then the same warp selection as C == 3
+        lib = _C.lib()
+        ws = torch.empty(lib.l3d_knn_features_ws_bytes(B, C, N), dtype=torch.uint8, device=x.device)
+        with _C.on_device(x.device):
+            _C.check(lib.l3d_knn_features(_C.ptr(x), B, C, N, k, _C.ptr(idx), _C.ptr(ws), _C.stream()), "knn")
+        return idx
     with _C.on_device(x.device):
         _C.check(_C.lib().l3d_knn_expansion(_C.ptr(x), B, N, k, _C.ptr(idx), _C.ptr(None),
                                             _C.stream()), "knn")

@@ -215,7 +215,6 @@ def test_error_codes():
     x = torch.rand(1, 3, 16, device=_dev())
     with pytest.raises(RuntimeError):
         knn(x, 17)                                   # k > N, like torch.topk
-    with pytest.raises(NotImplementedError):
-        knn(torch.rand(1, 64, 16, device=_dev()), 4)  # feature-space kNN is a 'next' row
+    assert knn(torch.rand(1, 64, 16, device=_dev()), 4).shape == (1, 16, 4)   # feature-space kNN (test_gpu_knn_features.py)
     rc = _C.lib().l3d_knn_expansion(_C.ptr(None), 1, 16, 4, _C.ptr(None), _C.ptr(None), _C.stream())
     assert rc == -1
