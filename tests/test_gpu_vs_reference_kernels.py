@@ -117,6 +117,24 @@ def test_against_reference_cuda_kernels(oracle_mod):
     rows.append(("get_graph_feature C2 (ref = torch ops on GPU)", _time(lambda: ref_torch.get_graph_feature(x, 20), 20, 3),
                  _time(lambda: __import__("learning3d_b200").utils.get_graph_feature(x, 20), 20, 3)))
 
+    # feature-space graphs (PRNet's dynamic DGCNN): same torch op sequence, C = 64 / 128
+    for C in (64, 128):
+        xf = torch.randn(32, C, 1024, device=DEV)
+        rows.append(("knn() features B32 C%d N1024 k20 (ref = torch matmul+topk on GPU)" % C,
+                     _time(lambda: ref_torch.knn(xf, 20), 10, 2), _time(lambda: knn(xf, 20), 10, 2)))
+    # DCP SVD head front half (svd.py:23-28): the reference's three torch ops vs the fused tcgen05 kernel
+    import math
+    from learning3d_b200.utils.svd import soft_correspondence
+    es = torch.randn(32, 512, 1024, device=DEV); et = torch.randn(32, 512, 1024, device=DEV)
+    tg = torch.rand(32, 3, 1024, device=DEV)
+
+    def ref_front():
+        sc = torch.matmul(es.transpose(2, 1).contiguous(), et) / math.sqrt(512)
+        sc = torch.softmax(sc, dim=2)
+        return torch.matmul(tg, sc.transpose(2, 1).contiguous())
+    rows.append(("SVDHead front C3 B32 d512 N1024 (ref = torch matmul+softmax+matmul on GPU)",
+                 _time(ref_front, 10, 2), _time(lambda: soft_correspondence(es, et, tg), 10, 2)))
+
     table = [{"op": n, "reference_us": round(r, 2), "ours_us": round(o, 2), "speedup": round(r / o, 2)} for n, r, o in rows]
     for t in table:
         print(json.dumps(t))
