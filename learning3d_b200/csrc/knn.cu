@@ -43,6 +43,12 @@ constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
 #ifndef L3D_KNN_R
 #define L3D_KNN_R 2
 #endif
+#ifndef L3D_KNN_PDL
+#define L3D_KNN_PDL 1        // programmatic dependent launch between consecutive kNN launches
+#endif
+#ifndef L3D_KNN_DEFER_QW
+#define L3D_KNN_DEFER_QW 1   // keep "- |q|^2" out of the register keys of the expansion mode (knn_rows_v2)
+#endif
 // Selection variants that were measured and dropped (profiles/r01): rank-by-counting
 // against the shared-memory survivor list (40.9 us), an FMNMX key/value network with tie fallback
 // (37.2 us) — both slower than the 64-bit composite network below (36.1 us at C2).
@@ -391,13 +397,21 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
   for (int r = 0; r < R; ++r) { base[r] = 0; kth[r] = -INFINITY; ovf[r] = (p.force_slow != 0); best[r] = 0ull; }
 
   for (int t = 0; t < ntiles; ++t) {
+    // DEFER: the register copy of an expansion key leaves out the final "- |q|^2".  s -> RN(s - |q|^2)
+    // is monotone, the registers only feed the threshold and the survivor mask (survivors are
+    // re-evaluated with the full formula below), so the selection stays exact as long as the s-space
+    // threshold is lowered to cover every s that can round to the k-th key (thr computation below).
+    constexpr bool DEFER = (L3D_KNN_DEFER_QW != 0) && MODE == MODE_EXPANSION_NEG;
     float d[R][32];
     const float4* pt = packed + t * KNN_TILE + lane;
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const float4 c = pt[e * 32];
 #pragma unroll
-      for (int r = 0; r < R; ++r) d[r][e] = knn_key<MODE>(q[r], c);
+      for (int r = 0; r < R; ++r) {
+        if (DEFER) d[r][e] = fmaf(2.0f, fmaf(q[r].z, c.z, fmaf(q[r].y, c.y, __fmul_rn(q[r].x, c.x))), -c.w);
+        else d[r][e] = knn_key<MODE>(q[r], c);
+      }
     }
     float mx[R];
 #pragma unroll
@@ -411,7 +425,17 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
     int cnt[R], incl[R], total[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float thr = fmaxf(__shfl_sync(L3D_FULL_MASK, mx[r], k - 1), kth[r]);
+      float thr = __shfl_sync(L3D_FULL_MASK, mx[r], k - 1);
+      if (DEFER) {
+        // kb: the exact key every survivor must reach (k-th lane maximum in key space, or the running
+        // k-th best).  K(s) >= kb implies s >= kb + |q|^2 - ulp(kb)/2, so rounding that bound DOWN
+        // (twice, with |kb| 2^-23 >= ulp/2 as the margin) keeps every such s; it admits at most the
+        // few s within ~2 ulp below, which the exact re-evaluation sorts out.
+        const float kb = fmaxf(__fsub_rn(thr, q[r].w), kth[r]);
+        thr = __fadd_rd(__fadd_rd(kb, q[r].w), -__fmul_rn(fmaxf(fabsf(kb), 1e-30f), 1.1920929e-7f));
+      } else {
+        thr = fmaxf(thr, kth[r]);
+      }
       // survivor mask: bit e = (d[e] >= thr).  d - thr is +0 on equality, so the survivors are the
       // differences with a clear sign bit; one FADD (FMA pipe) + one funnel shift (ALU pipe) per key
       // instead of FSETP + predicated OR (two ALU-pipe instructions; the ALU pipe is the busier one).
@@ -514,6 +538,12 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   }
   __syncthreads();
   uint32_t parity = 0;
+#if L3D_KNN_PDL
+  // programmatic dependent launch: let the next launch on the stream start filling SMs as our CTAs
+  // retire, and do not touch global memory before the previous launch has fully completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
   const long rows_total = (long)p.B * M;
   const long r0 = rows_total * blockIdx.x / gridDim.x;
@@ -636,7 +666,21 @@ static int knn_launch_t(KnnParams p, cudaStream_t stream) {
   const long max_useful = (rows + KNN_WARPS - 1) / KNN_WARPS;
   if (grid > max_useful) grid = max_useful;
   if (grid < 1) grid = 1;
+#if L3D_KNN_PDL
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(KNN_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) return (int)le;
+  }
+#else
   kern<<<(unsigned)grid, KNN_THREADS, smem, stream>>>(p);
+#endif
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
