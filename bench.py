@@ -273,6 +273,8 @@ def run_ours(args, rank, local_rank, world):
         extra.update(chamfer_bench(torch, dev, dist_on, world, 5 if args.profile else 200))
     except ImportError:
         pass
+    if world == 1:
+        extra.update(tensor_core_bench(torch, dev, 2 if args.profile else 30))
 
     if rank == 0:
         pairs_per_step = world * B * N * N
@@ -351,6 +353,34 @@ def chamfer_bench(torch, dev, dist_on, world, iters=200):
             ms = float(t.item())
         out["chamfer_fwd_bwd_clouds_per_sec_B%d" % B] = world * B / (ms * 1e-3)
         out["chamfer_fwd_bwd_ms_B%d" % B] = ms
+    return out
+
+
+def tensor_core_bench(torch, dev, iters=30):
+    """Tensor-core rows of the path (per GPU, not aggregated): DCP SVD-head front half at C3
+    (B=32, d_k=512, N=1024; svd.py:23-28 fused) and the feature-space kNN graph (B=32, C=64, N=1024, k=20)."""
+    from learning3d_b200.utils import knn
+    from learning3d_b200.utils.svd import soft_correspondence
+    out = {}
+    es = torch.randn(32, 512, 1024, device=dev)
+    et = torch.randn(32, 512, 1024, device=dev)
+    tg = torch.rand(32, 3, 1024, device=dev)
+    xf = torch.randn(32, 64, 1024, device=dev)
+    for name, fn, flop in (("svd_head_front_C3", lambda: soft_correspondence(es, et, tg), 2.0 * 32 * 1024 * 1024 * 512),
+                           ("knn_features_C64", lambda: knn(xf, 20), None)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name + "_us"] = ms * 1e3
+        if flop:
+            out[name + "_fp32_equiv_tflops"] = flop / (ms * 1e-3) / 1e12
     return out
 
 
