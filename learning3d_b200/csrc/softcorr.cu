@@ -534,14 +534,17 @@ static int g_softcorr_force_generic = 0;
 template <int EPI>
 static int sc_launch(SoftCorrParams p, void* stream) {
   if (p.B > 65535) return L3D_ERR_UNSUPPORTED;
-  static bool attr_set = false;
+  // the opt-in shared-memory size is a per-device function attribute: cache per (thread, device)
+  static thread_local int attr_dev = -1;
   const size_t smem_t = softcorr_smem_bytes<true>(), smem_g = softcorr_smem_bytes<false>();
-  if (!attr_set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(softcorr_kernel<false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_dev = dev;
   }
   p.c = (float)(1.4426950408889634 / sqrt((double)p.D));
   void* errp = nullptr;
@@ -580,7 +583,7 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
 
 // ---- feature-space kNN: knn() of utils/model_common_utils.py:3-9 for C != 3 -----------------------------
 // xx[b,n] = sum_c x[b,c,n]^2, accumulated in channel order (torch.sum(x**2, dim=1), :6)
-__global__ void sqnorm_kernel(const float* __restrict__ x, int B, int C, int N, float* __restrict__ xx) {
+static __global__ void sqnorm_kernel(const float* __restrict__ x, int B, int C, int N, float* __restrict__ xx) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long)B * N) return;
   const int b = (int)(t / N), n = (int)(t - (long)b * N);
