@@ -46,6 +46,9 @@ constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
 #ifndef L3D_KNN_PDL
 #define L3D_KNN_PDL 1        // programmatic dependent launch between consecutive kNN launches
 #endif
+#ifndef L3D_KNN_ALIGN_GRID
+#define L3D_KNN_ALIGN_GRID 0 // grid = multiple of B (no CTA stages two clouds): measured 34.7 vs 33.4 us, off
+#endif
 #ifndef L3D_KNN_DEFER_QW
 #define L3D_KNN_DEFER_QW 1   // keep "- |q|^2" out of the register keys of the expansion mode (knn_rows_v2)
 #endif
@@ -665,6 +668,14 @@ static int knn_launch_t(KnnParams p, cudaStream_t stream) {
   long grid = (long)sm_count() * occ;          // persistent-style: every CTA resident at once
   const long max_useful = (rows + KNN_WARPS - 1) / KNN_WARPS;
   if (grid > max_useful) grid = max_useful;
+#if L3D_KNN_ALIGN_GRID
+  // A CTA whose row range crosses a batch item stages two clouds (two prologues on the critical path).
+  // When a multiple of B is within 5 % of the resident grid, use it: ranges then never cross an item.
+  if (grid > p.B) {
+    const long g2 = grid / p.B * p.B;
+    if (g2 * 20 >= grid * 19) grid = g2;
+  }
+#endif
   if (grid < 1) grid = 1;
 #if L3D_KNN_PDL
   {
@@ -694,6 +705,9 @@ static int knn_launch(KnnParams p, cudaStream_t stream) {
   if (p.N > L3D_KNN_MAX_N || p.k > 128) return L3D_ERR_UNSUPPORTED;
   p.force_slow = g_force_slow;
   p.use_tma = ((reinterpret_cast<uintptr_t>(p.cand) & 15u) == 0 && (p.N & 3) == 0) ? 1 : 0;
+#ifdef L3D_KNN_FORCE_NO_TMA   // experiment knob (profiles/build_variants.sh): plain-load staging
+  p.use_tma = 0;
+#endif
   // Heavy selections out of a small cloud (FlowNet3D's flow embedding: k = 64 of N = 256) sort the
   // whole row instead of thresholding it.
   if (p.N <= KNN_SORT_MAX_N && p.k * 8 >= p.N) {
