@@ -299,8 +299,9 @@ int l3d_soft_correspondence(const float* src_emb_dev, const float* tgt_emb_dev, 
  * l3d_soft_correspondence (0 = ok, 1/2/3 = a bounded mbarrier wait of the epilogue / producer /
  * MMA-issuer role ran out), or a CUDA error code. */
 int l3d_soft_correspondence_status(void);
-/* Testing hook: nonzero forces the generic (LDG producer, any shape) operand pipeline even when the
- * shape is eligible for the TMA pipeline (Ns, Nt multiples of 4, 16-byte aligned embeddings). */
+/* Testing hook for the operand pipeline of l3d_soft_correspondence / l3d_knn_features:
+ *   0 = automatic (TMA + CTA pairs when eligible: Ns, Nt multiples of 4, 16-byte aligned embeddings, Ns > 128),
+ *   1 = force the generic (LDG producer, any shape) pipeline,  2 = TMA pipeline without CTA pairs. */
 void l3d_debug_soft_correspondence_force_generic(int on);
 /* Debug aid: shared-memory image (4 x 4096 floats: A_hi, A_lo, B_hi, B_lo) of the first pipeline stage of
  * CTA (0,0) in the last l3d_debug_soft_correspondence_scores launch on the TMA path -> host_out. */

@@ -45,19 +45,23 @@ constexpr int SC_EPI_THREADS = 128;
 constexpr int SC_PROD_THREADS = 128;
 constexpr int SC_THREADS = SC_EPI_THREADS + SC_PROD_THREADS + 64;   // + MMA warp + TMA warp
 constexpr uint32_t SC_SPIN_LIMIT = 1u << 22;
-constexpr int SC_MAX_BN = 256, SC_MAX_STAGES = 4;
+constexpr int SC_MAX_BN = 256, SC_MAX_STAGES = 6;
 
 // Tile configuration per operand pipeline.  The kernel is shared-memory-bandwidth bound (TMA writes,
 // the splitters' read + write and the tensor core's operand reads all cross the same 128 B/clk port), so
 // the TMA path uses N = 256 MMAs: A is read once per 256 target points instead of once per 128.
-template <bool USE_TMA>
+// CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x 256 tile per MMA; each CTA keeps
+// its own 128 source rows and only HALF of the target columns, so the B-side TMA, split and operand-read
+// traffic per SM halves (144 KB -> 96 KB of shared-memory traffic per 16-channel stage).
+template <bool USE_TMA, int CTAS = 1>
 struct SoftCorrCfg {
   static constexpr int BN = USE_TMA ? 256 : 128;      // target points per tile (UMMA N)
   static constexpr int BK = USE_TMA ? 16 : 32;        // embedding channels per stage
-  static constexpr int STAGES = USE_TMA ? 4 : 3;
+  static constexpr int STAGES = USE_TMA ? (CTAS == 2 ? 6 : 4) : 3;
+  static constexpr int BN_LOCAL = BN / CTAS;          // target columns whose operands live in this CTA
   static constexpr int A_TILE = SC_BM * BK * 4;       // bytes: 8 KB / 16 KB
-  static constexpr int B_TILE = BN * BK * 4;          // bytes: 16 KB
-  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;   // A_hi, A_lo, B_hi, B_lo: 48 KB / 64 KB
+  static constexpr int B_TILE = BN_LOCAL * BK * 4;    // bytes: 16 KB (8 KB in a pair)
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;   // A_hi, A_lo, B_hi, B_lo: 48 / 32 / 64 KB
   static constexpr int TMEM_COLS = 2 * BN;            // two fp32 accumulators
   static constexpr int ATOM = 32 * BK * 4;            // TMA path: bytes of one [BK d x 32 n] box
 };
@@ -109,6 +113,58 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- CTA-pair (cluster of 2) variants -----------------------------------------------------------
+// wait with cluster-scope acquire: the phase is completed by arrivals from the peer CTA as well
+__device__ __forceinline__ bool mbar_wait_bounded_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < SC_SPIN_LIMIT; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on the barrier in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -190,8 +246,8 @@ __device__ __forceinline__ uint64_t sc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = bn;
 // mn_major sets a_major = b_major = MN
-__host__ __device__ constexpr uint32_t sc_idesc(int bn, bool mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(SC_BM >> 4) << 24) |
+__host__ __device__ constexpr uint32_t sc_idesc(int bn, bool mn_major, int m = SC_BM) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24) |
          (mn_major ? ((1u << 15) | (1u << 16)) : 0u);
 }
 constexpr int SC_GBK = SoftCorrCfg<false>::BK;   // generic pipeline: channels per stage (one 128 B swizzle row)
@@ -228,13 +284,16 @@ __device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile,
 constexpr int EPI_SOFTMAX_XYZ = 0;   // SVD head: online softmax, xyz-weighted sums  -> out [B,3,Ns]
 constexpr int EPI_KEYS = 1;          // feature-space kNN: negated expansion distances -> keys [B,Ns,Nt]
 
-template <bool USE_TMA, int EPI>
+template <bool USE_TMA, int EPI, int CTAS = 1>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap_a,
                 const __grid_constant__ CUtensorMap tmap_b) {
-  using Cfg = SoftCorrCfg<USE_TMA>;
+  static_assert(CTAS == 1 || (CTAS == 2 && USE_TMA), "CTA pairs exist on the TMA pipeline only");
+  using Cfg = SoftCorrCfg<USE_TMA, CTAS>;
   constexpr int SC_BN = Cfg::BN, SC_BK = Cfg::BK, SC_STAGES = Cfg::STAGES, SC_STAGE_BYTES = Cfg::STAGE;
   constexpr int A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE, SC_TMEM_COLS = Cfg::TMEM_COLS;
+  constexpr bool PAIR = (CTAS == 2);
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // rank 0 of a pair issues the MMAs
   extern __shared__ unsigned char sc_raw[];
   // 1024-byte alignment: the swizzle XOR is applied to absolute shared addresses
   unsigned char* tiles = reinterpret_cast<unsigned char*>(
@@ -252,21 +311,31 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
   if (tid == 0) {
     for (int s = 0; s < SC_STAGES; ++s) {
       mbar_init(&sh->tma_full[s], 1);
-      mbar_init(&sh->full[s], SC_PROD_THREADS);
+      // in a pair the leader's full / acc_empty barriers also collect the peer's splitters / epilogue
+      mbar_init(&sh->full[s], SC_PROD_THREADS * CTAS);
       mbar_init(&sh->empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS * CTAS); }
     fence_mbar_init();
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(&sh->tmem_base)),
-                 "n"(SC_TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(&sh->tmem_base)),
+                   "n"(SC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(&sh->tmem_base)),
+                   "n"(SC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
 
@@ -355,7 +424,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
       tc_fence_before();
-      mbar_arrive(&sh->acc_empty[a]);
+      if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);   // the leader's MMA warp waits for both epilogues
+      else mbar_arrive(&sh->acc_empty[a]);
     }
     if (!ok) atomicCAS(p.err, 0, 1);
     if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns) {
@@ -395,7 +465,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             g_softcorr_dbg_tiles[w] = *reinterpret_cast<const float*>(tiles + s * SC_STAGE_BYTES + w * 4);
         }
         fence_proxy_async();
-        mbar_arrive(&sh->full[s]);
+        if (PAIR) mbar_arrive_cluster(&sh->full[s], 0);   // the leader's MMA reads both CTAs' tiles
+        else mbar_arrive(&sh->full[s]);
       }
     } else {
       // -------------------------------------------- generic producers: LDG, split, K-major swizzled STS
@@ -421,34 +492,48 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     // ------------------------------------------------ MMA issuer
     bool ok = true;
     int it = 0;
-    for (int jb = 0; jb < num_jb && ok; ++jb) {
+    // in a pair only rank 0 issues: its MMAs (cta_group::2, M = 256) read A and half of B from EACH CTA's
+    // shared memory and write each CTA's 128 accumulator rows into that CTA's tensor memory
+    for (int jb = 0; jb < num_jb && ok && crank == 0; ++jb) {
       const int a = jb & 1;
-      if (!mbar_wait_bounded(&sh->acc_empty[a], (uint32_t)(((jb >> 1) & 1) ^ 1))) { ok = false; break; }
+      const uint32_t pe = (uint32_t)(((jb >> 1) & 1) ^ 1);
+      if (!(PAIR ? mbar_wait_bounded_cluster(&sh->acc_empty[a], pe) : mbar_wait_bounded(&sh->acc_empty[a], pe))) { ok = false; break; }
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)(a * SC_BN);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % SC_STAGES;
         const uint32_t n = (uint32_t)(it / SC_STAGES);
-        if (!mbar_wait_bounded(&sh->full[s], n & 1u)) { ok = false; break; }
+        if (!(PAIR ? mbar_wait_bounded_cluster(&sh->full[s], n & 1u) : mbar_wait_bounded(&sh->full[s], n & 1u))) { ok = false; break; }
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = tiles_s + s * SC_STAGE_BYTES;
           // MN-major tf32 operands exist only in the 32-byte-atom flavour of the 128 B swizzle
           // (UMMA layout 1 = TMA SWIZZLE_128B_ATOM_32B): 4-channel groups 512 B apart.
           const uint32_t lbo = USE_TMA ? (uint32_t)Cfg::ATOM : 16u, sbo = USE_TMA ? 512u : 1024u, lay = USE_TMA ? 1u : 2u;
-          constexpr uint32_t idesc = sc_idesc(SC_BN, USE_TMA);
+          constexpr uint32_t idesc = sc_idesc(SC_BN, USE_TMA, SC_BM * CTAS);
           const uint64_t a_hi = sc_desc(sa, lbo, sbo, lay), a_lo = sc_desc(sa + A_TILE, lbo, sbo, lay);
           const uint64_t b_hi = sc_desc(sa + 2 * A_TILE, lbo, sbo, lay), b_lo = sc_desc(sa + 2 * A_TILE + B_TILE, lbo, sbo, lay);
 #pragma unroll
           for (int k = 0; k < SC_BK / SC_UK; ++k) {
             // K-major: +32 bytes inside the 128 B swizzle row; MN-major: next 8-channel group (+1024 B)
             const uint64_t adv = (uint64_t)((USE_TMA ? k * 1024 : k * SC_UK * 4) >> 4);
-            tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-            tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            if (PAIR) {
+              tc_mma_tf32_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              tc_mma_tf32_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
-          tc_commit(&sh->empty[s]);
-          if (kb == num_kb - 1) tc_commit(&sh->acc_full[a]);
+          if (PAIR) {
+            tc_commit_pair(&sh->empty[s]);                       // frees the stage in both CTAs
+            if (kb == num_kb - 1) tc_commit_pair(&sh->acc_full[a]);
+          } else {
+            tc_commit(&sh->empty[s]);
+            if (kb == num_kb - 1) tc_commit(&sh->acc_full[a]);
+          }
         }
         __syncwarp();
       }
@@ -468,9 +553,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
         for (int q = 0; q < SC_BM / 32; ++q)
           tma_load_3d(st + q * Cfg::ATOM, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+        // a pair member fetches only its half of the 256 target columns
 #pragma unroll
-        for (int q = 0; q < SC_BN / 32; ++q)
-          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, jb * SC_BN + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+        for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
+          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, jb * SC_BN + (int)crank * Cfg::BN_LOCAL + 32 * q,
+                      kb * SC_BK, b, &sh->tma_full[s]);
       }
       __syncwarp();
     }
@@ -479,16 +566,19 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer may still be arriving on our barriers / its MMAs reading our tiles
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SC_TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SC_TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SC_TMEM_COLS) : "memory");
   }
 }
 
-template <bool USE_TMA>
+template <bool USE_TMA, int CTAS = 1>
 size_t softcorr_smem_bytes() {
-  return (size_t)SoftCorrCfg<USE_TMA>::STAGES * SoftCorrCfg<USE_TMA>::STAGE + sizeof(SoftCorrShared) + 1024;
+  return (size_t)SoftCorrCfg<USE_TMA, CTAS>::STAGES * SoftCorrCfg<USE_TMA, CTAS>::STAGE + sizeof(SoftCorrShared) + 1024;
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------
@@ -537,12 +627,15 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   // the opt-in shared-memory size is a per-device function attribute: cache per (thread, device)
   static thread_local int attr_dev = -1;
   const size_t smem_t = softcorr_smem_bytes<true>(), smem_g = softcorr_smem_bytes<false>();
+  const size_t smem_p = softcorr_smem_bytes<true, 2>();
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(softcorr_kernel<true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(softcorr_kernel<false, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(softcorr_kernel<true, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
     if (e != cudaSuccess) return (int)e;
     attr_dev = dev;
   }
@@ -554,12 +647,26 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   dim3 grid((p.Ns + SC_BM - 1) / SC_BM, p.B);
 
   // TMA needs 16-byte global strides and bases
-  bool tma = !g_softcorr_force_generic && (p.Ns % 4 == 0) && (p.Nt % 4 == 0) &&
+  bool tma = g_softcorr_force_generic != 1 && (p.Ns % 4 == 0) && (p.Nt % 4 == 0) &&
              (((uintptr_t)p.src_emb | (uintptr_t)p.tgt_emb) & 15) == 0;
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
   if (tma) tma = make_emb_tmap(&ma, p.src_emb, p.B, p.D, p.Ns) && make_emb_tmap(&mb, p.tgt_emb, p.B, p.D, p.Nt);
-  if (tma)
+  if (tma && g_softcorr_force_generic != 2 && p.Ns > SC_BM) {
+    // CTA pairs: cluster (2,1,1), two adjacent 128-row blocks of one batch item (an odd last block gets an
+    // all-out-of-range partner: TMA zero-fills its tiles and its epilogue stores nothing)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ((p.Ns + 2 * SC_BM - 1) / (2 * SC_BM)), p.B);
+    cfg.blockDim = dim3(SC_THREADS);
+    cfg.dynamicSmemBytes = smem_p;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, softcorr_kernel<true, EPI, 2>, p, ma, mb);
+    if (le != cudaSuccess) return (int)le;
+  } else if (tma)
     softcorr_kernel<true, EPI><<<grid, SC_THREADS, smem_t, (cudaStream_t)stream>>>(p, ma, mb);
   else
     softcorr_kernel<false, EPI><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);

@@ -50,6 +50,8 @@ torch.manual_seed(0)
 MODE = "tma"
 if len(sys.argv) > 1 and sys.argv[1] == "generic":
     MODE = "generic"; lib.l3d_debug_soft_correspondence_force_generic(1)
+if len(sys.argv) > 1 and sys.argv[1] == "tma1":
+    MODE = "tma1"; lib.l3d_debug_soft_correspondence_force_generic(2)
 print("operand pipeline:", MODE)
 # E1: one tile, one K block
 B, D, N = 1, 32, 128

@@ -1,5 +1,5 @@
 """GPU: fused soft-correspondence kernel (tcgen05 3xTF32 + online softmax) against fp64 evaluation of
-utils/svd.py:23-28, on both operand pipelines (TMA MN-major / generic LDG K-major).
+utils/svd.py:23-28, on all three operand pipelines (TMA MN-major with CTA pairs / TMA single CTA / generic LDG K-major).
 
 Tolerances (stated, floating point): raw scores within 4e-6 * sum_d |a_d||b_d| of fp64 (3xTF32 keeps ~21
 mantissa bits per product; the fp32 SGEMM the reference calls is in the same class), src_corr within 2e-5
@@ -34,10 +34,11 @@ def _run_debug(src_emb, tgt_emb, tgt):
     return out, sc
 
 
-@pytest.fixture(params=["tma", "generic"])
+@pytest.fixture(params=["auto", "generic", "tma_single_cta"])
 def pipeline(request):
+    """auto = TMA operands + CTA pairs (tcgen05 cta_group::2) when eligible; the other two force a fallback."""
     from learning3d_b200 import _C
-    _C.lib().l3d_debug_soft_correspondence_force_generic(1 if request.param == "generic" else 0)
+    _C.lib().l3d_debug_soft_correspondence_force_generic({"auto": 0, "generic": 1, "tma_single_cta": 2}[request.param])
     yield request.param
     _C.lib().l3d_debug_soft_correspondence_force_generic(0)
 
