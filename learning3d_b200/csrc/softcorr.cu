@@ -312,10 +312,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     for (int s = 0; s < SC_STAGES; ++s) {
       mbar_init(&sh->tma_full[s], 1);
       // in a pair the leader's full / acc_empty barriers also collect the peer's splitters / epilogue
-      mbar_init(&sh->full[s], SC_PROD_THREADS * CTAS);
+      // (one arrival per warp: every lane fences, __syncwarp orders them, lane 0 arrives)
+      mbar_init(&sh->full[s], SC_PROD_THREADS / 32 * CTAS);
       mbar_init(&sh->empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS * CTAS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], SC_EPI_THREADS / 32 * CTAS); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -424,8 +425,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         }
       }
       tc_fence_before();
-      if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);   // the leader's MMA warp waits for both epilogues
-      else mbar_arrive(&sh->acc_empty[a]);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);   // the leader's MMA warp waits for both epilogues
+        else mbar_arrive(&sh->acc_empty[a]);
+      }
     }
     if (!ok) atomicCAS(p.err, 0, 1);
     if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns) {
@@ -465,8 +469,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             g_softcorr_dbg_tiles[w] = *reinterpret_cast<const float*>(tiles + s * SC_STAGE_BYTES + w * 4);
         }
         fence_proxy_async();
-        if (PAIR) mbar_arrive_cluster(&sh->full[s], 0);   // the leader's MMA reads both CTAs' tiles
-        else mbar_arrive(&sh->full[s]);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&sh->full[s], 0);   // the leader's MMA reads both CTAs' tiles
+          else mbar_arrive(&sh->full[s]);
+        }
       }
     } else {
       // -------------------------------------------- generic producers: LDG, split, K-major swizzled STS
@@ -484,7 +491,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         sc_store_row(st, st + A_TILE, r, va);
         sc_store_row(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, r, vb);
         fence_proxy_async();
-        mbar_arrive(&sh->full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->full[s]);
       }
     }
     if (!ok) atomicCAS(p.err, 0, 2);

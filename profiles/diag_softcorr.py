@@ -111,7 +111,9 @@ def theirs():
     s = torch.matmul(a.transpose(2, 1).contiguous(), b) / math.sqrt(D)
     s = torch.softmax(s, dim=2)
     return torch.matmul(t, s.transpose(2, 1).contiguous())
-for name, fn in (("fused tcgen05", ours), ("torch fp32 (reference ops)", theirs)):
+def ours_single():
+    lib.l3d_debug_soft_correspondence_force_generic(2); ours(); lib.l3d_debug_soft_correspondence_force_generic(0)
+for name, fn in (("fused tcgen05 (auto: CTA pairs)", ours), ("fused tcgen05 (single CTA)", ours_single), ("torch fp32 (reference ops)", theirs)):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
