@@ -115,7 +115,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // ---- CTA-pair (cluster of 2) variants -----------------------------------------------------------
-// wait with cluster-scope acquire: the phase is completed by arrivals from the peer CTA as well
+// wait on a barrier whose phase is completed by arrivals from the peer CTA as well (same PTX as the
+// CTA-local wait, like cutlass::arch::ClusterBarrier::wait; kept separate to mark the cross-CTA sites)
 __device__ __forceinline__ bool mbar_wait_bounded_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
@@ -123,7 +124,7 @@ __device__ __forceinline__ bool mbar_wait_bounded_cluster(uint64_t* bar, uint32_
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(addr), "r"(parity)
@@ -132,12 +133,15 @@ __device__ __forceinline__ bool mbar_wait_bounded_cluster(uint64_t* bar, uint32_
   }
   return false;
 }
-// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics, as
+// cutlass::arch::ClusterBarrier::arrive(cta_id): the writes it publishes were already forced into shared memory
+// by fence.proxy.async; an explicit .release.cluster here stalled every splitter warp ~1.5k cycles per stage
+// (266 us vs 128 us for the kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
