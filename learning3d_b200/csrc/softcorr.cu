@@ -136,7 +136,7 @@ __device__ __forceinline__ bool mbar_wait_bounded_cluster(uint64_t* bar, uint32_
 // arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics, as
 // cutlass::arch::ClusterBarrier::arrive(cta_id): the writes it publishes were already forced into shared memory
 // by fence.proxy.async; an explicit .release.cluster here stalled every splitter warp ~1.5k cycles per stage
-// (266 us vs 128 us for the kernel).
+// (266 us vs 152 us for the C3 kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
