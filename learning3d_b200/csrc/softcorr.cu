@@ -89,6 +89,9 @@ struct SoftCorrShared {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  // EPI_KEYS: per-warp 32 x 32 transpose tile (row stride 36 floats: conflict-free 16-byte accesses both
+  // ways) so that the key matrix is written as full 128-byte lines instead of 16-byte pieces of 32 rows
+  alignas(16) float tbuf[SC_EPI_THREADS / 32][32][36];
 };
 
 __device__ int g_softcorr_error = 0;
@@ -385,25 +388,37 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         if (EPI == EPI_KEYS) {
           // pd = ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2  (model_common_utils.py:5-7, same association as knn.cu);
           // thread = row i: 32 consecutive floats of its key row, 16-byte stores when the row allows
-          if (i < p.Ns) {
-            const float4* xz = &sh->xyz[a][ch * 32];
-            float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32;
-            const int nv = min(32, nvalid - ch * 32);
-            if (nv == 32 && (p.Nt & 3) == 0) {
+          const float4* xz = &sh->xyz[a][ch * 32];
+          const int nv = min(32, nvalid - ch * 32);
+          if (nv == 32 && (p.Nt & 3) == 0) {
+            // full chunk: transpose the warp's 32 x 32 block through shared memory, then every store
+            // instruction writes four complete 128-byte lines (8 lanes x 16 B per row)
+            float(*tb)[36] = sh->tbuf[warp];
 #pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                float4 o;
-                o.x = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
-                o.y = __fsub_rn(fmaf(2.0f, v[e + 1], -xz[e + 1].x), xi);
-                o.z = __fsub_rn(fmaf(2.0f, v[e + 2], -xz[e + 2].x), xi);
-                o.w = __fsub_rn(fmaf(2.0f, v[e + 3], -xz[e + 3].x), xi);
-                *reinterpret_cast<float4*>(dst + e) = o;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (e < nv) dst[e] = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
+            for (int e = 0; e < 32; e += 4) {
+              float4 o;
+              o.x = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
+              o.y = __fsub_rn(fmaf(2.0f, v[e + 1], -xz[e + 1].x), xi);
+              o.z = __fsub_rn(fmaf(2.0f, v[e + 2], -xz[e + 2].x), xi);
+              o.w = __fsub_rn(fmaf(2.0f, v[e + 3], -xz[e + 3].x), xi);
+              *reinterpret_cast<float4*>(&tb[lane][e]) = o;
             }
+            __syncwarp();
+            const int rr = lane >> 3, cc = (lane & 7) * 4;
+            const int ibase = i0 + warp * 32;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(&tb[r + rr][cc]);
+              const int ir = ibase + r + rr;
+              if (ir < p.Ns)
+                *reinterpret_cast<float4*>(p.keys + ((size_t)b * p.Ns + ir) * p.Nt + j0 + ch * 32 + cc) = o;
+            }
+            __syncwarp();
+          } else if (i < p.Ns) {
+            float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nv) dst[e] = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
           }
           continue;
         }
@@ -702,17 +717,30 @@ static int softcorr_launch(const float* src_emb, const float* tgt_emb, const flo
 
 // ---- feature-space kNN: knn() of utils/model_common_utils.py:3-9 for C != 3 -----------------------------
 // xx[b,n] = sum_c x[b,c,n]^2, accumulated in channel order (torch.sum(x**2, dim=1), :6)
+// 256 threads = 32 points x 8 channel slices: coalesced over points, 8 partial sums per point combined
+// in slice order (deterministic; the row is toleranced anyway, §3.7)
 static __global__ void sqnorm_kernel(const float* __restrict__ x, int B, int C, int N, float* __restrict__ xx) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long)B * N) return;
-  const int b = (int)(t / N), n = (int)(t - (long)b * N);
-  const float* p = x + (size_t)b * C * N + n;
+  __shared__ float part[8][33];
+  const int ln = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long t = (long)blockIdx.x * 32 + ln;            // flattened (b, n)
   float acc = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float v = __ldg(p + (size_t)c * N);
-    acc = __fadd_rn(acc, __fmul_rn(v, v));
+  if (t < (long)B * N) {
+    const int b = (int)(t / N), n = (int)(t - (long)b * N);
+    const float* p = x + (size_t)b * C * N + n;
+    const int c0 = (int)((long)C * sl / 8), c1 = (int)((long)C * (sl + 1) / 8);
+    for (int c = c0; c < c1; ++c) {
+      const float v = __ldg(p + (size_t)c * N);
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
   }
-  xx[t] = acc;
+  part[sl][ln] = acc;
+  __syncthreads();
+  if (sl == 0 && t < (long)B * N) {
+    float s = part[0][ln];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s = __fadd_rn(s, part[k][ln]);
+    xx[t] = s;
+  }
 }
 
 static size_t knn_features_keys_bytes(int B, int N) {
@@ -734,7 +762,7 @@ extern "C" int l3d_knn_features(const float* x_dev, int B, int C, int N, int k, 
   float* keys = reinterpret_cast<float*>(ws_dev);
   float* xx = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws_dev) + knn_features_keys_bytes(B, N));
   const long rows = (long)B * N;
-  sqnorm_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, B, C, N, xx);
+  sqnorm_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, (cudaStream_t)stream>>>(x_dev, B, C, N, xx);
   count_launch();
   L3D_LAUNCH_CHECK();
   SoftCorrParams p;
