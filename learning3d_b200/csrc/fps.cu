@@ -8,8 +8,8 @@
 // item keeps every point and its running min-distance in REGISTERS for the whole run, and a round
 // costs one distance update per register, one REDUX (__reduce_max_sync) warp arg-max on the distance
 // bits plus a tie-key pass, ONE __syncthreads (double-buffered per-warp results) and a redundant
-// per-warp final reduce — no global-memory traffic inside the loop except the 12-byte read of the newly
-// selected point (L1-resident).
+// per-warp final reduce — no global-memory traffic inside the loop at all: the coordinates of the newly
+// selected point come from a shared-memory copy of the cloud (12 bytes, LDS broadcast).
 //
 // Selection semantics reproduced exactly (indices are bit-identical on tie-free AND tied inputs):
 //   mode 0 (pointnet2 CUDA): d = nvcc-contracted fma form; per-thread strict '>' over k = tid, tid+bs, ...;
@@ -57,11 +57,19 @@ __device__ __forceinline__ bool fps_better(float av, uint32_t at, float bv, uint
 template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
   __shared__ uint2 s_r[2][FPS_WARPS];   // per-warp (max distance bits, ~tiekey), double-buffered
+  // The cloud also lives in shared memory: every round starts by reading the coordinates of the point
+  // selected by the previous one — a dependent access on the critical path of all N-1 rounds.  From
+  // global memory (a line this SM never touched through that path: an L2 round trip) a round took ~990
+  // cycles; an LDS broadcast is ~30.
+  extern __shared__ float s_xyz[];
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, M = p.M;
-  const float* xyz = p.xyz + (size_t)b * N * 3;
+  const float* gxyz = p.xyz + (size_t)b * N * 3;
+  for (int i = tid; i < 3 * N; i += FPS_THREADS) s_xyz[i] = gxyz[i];
+  __syncthreads();
+  const float* xyz = s_xyz;
 
   float px[PPT], py[PPT], pz[PPT], td[PPT];
   uint32_t tk[PPT];
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
   }
 
   for (int j = 1; j < M; ++j) {
-    const float cx = __ldg(xyz + old * 3), cy = __ldg(xyz + old * 3 + 1), cz = __ldg(xyz + old * 3 + 2);
+    const float cx = xyz[old * 3], cy = xyz[old * 3 + 1], cz = xyz[old * 3 + 2];   // LDS broadcast
     // Distances are >= +0, so their bit patterns order like unsigned integers: the arg-max is two
     // hardware warp reductions (REDUX.MAX.U32) — first the distance bits, then ~tiekey among the
     // lanes that hold the maximum — instead of a 5-step shuffle butterfly over three values.
@@ -154,11 +162,24 @@ static int fps_launch(FpsParams p, cudaStream_t s) {
   p.ref_log2 = 0;
   while ((1 << p.ref_log2) < bs) ++p.ref_log2;
   const int ppt = (p.N + FPS_THREADS - 1) / FPS_THREADS;
-  if (ppt <= 1) fps_kernel<1><<<p.B, FPS_THREADS, 0, s>>>(p);
-  else if (ppt <= 2) fps_kernel<2><<<p.B, FPS_THREADS, 0, s>>>(p);
-  else if (ppt <= 4) fps_kernel<4><<<p.B, FPS_THREADS, 0, s>>>(p);
-  else if (ppt <= 8) fps_kernel<8><<<p.B, FPS_THREADS, 0, s>>>(p);
-  else fps_kernel<16><<<p.B, FPS_THREADS, 0, s>>>(p);
+  const size_t smem = (size_t)p.N * 3 * sizeof(float);   // <= 96 KB (N <= 8192)
+  if (smem > 40 * 1024) {   // (static shared memory also counts against the 48 KB default)
+    // opt in to > 48 KB of dynamic shared memory (per device; only the two widest instantiations need it)
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+      cudaError_t e = cudaFuncSetAttribute(fps_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr_dev = dev;
+    }
+  }
+  if (ppt <= 1) fps_kernel<1><<<p.B, FPS_THREADS, smem, s>>>(p);
+  else if (ppt <= 2) fps_kernel<2><<<p.B, FPS_THREADS, smem, s>>>(p);
+  else if (ppt <= 4) fps_kernel<4><<<p.B, FPS_THREADS, smem, s>>>(p);
+  else if (ppt <= 8) fps_kernel<8><<<p.B, FPS_THREADS, smem, s>>>(p);
+  else fps_kernel<16><<<p.B, FPS_THREADS, smem, s>>>(p);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
