@@ -106,6 +106,21 @@ def main():
     R = torch.empty(32, 3, 3, device=DEV); t = torch.empty(32, 3, device=DEV)
     report("svd_head_tail B32 N1024", timeit(lambda: lib.l3d_svd_head_tail(_C.ptr(src), _C.ptr(corr), 32, 1024,
                                                                             _C.ptr(R), _C.ptr(t), _C.stream())))
+    # C3: SVD head front (soft correspondences, tcgen05) and the whole SVDHead.forward under no_grad
+    from learning3d_b200.utils.svd import soft_correspondence
+    es = torch.randn(32, 512, 1024, device=DEV); et = torch.randn(32, 512, 1024, device=DEV)
+    tg = torch.rand(32, 3, 1024, device=DEV)
+    us = timeit(lambda: soft_correspondence(es, et, tg), iters=50, warm=5)
+    report("soft_correspondence B32 d512 N1024", us, fp32_equiv_tflops=2.0 * 32 * 1024 * 1024 * 512 / us / 1e6)
+    head = SVDHead(512, input_shape="bnc").to(DEV)
+    srcp = torch.rand(32, 1024, 3, device=DEV); tgtp = torch.rand(32, 1024, 3, device=DEV)
+    with torch.no_grad():
+        report("SVDHead.forward B32 d512 N1024 (no_grad: fused front + Kabsch tail)",
+               timeit(lambda: head(es, et, srcp, tgtp), iters=50, warm=5))
+    # feature-space graphs (PRNet DGCNN)
+    for C in (64, 128):
+        xf = torch.randn(32, C, 1024, device=DEV)
+        report("knn features B32 C%d N1024 k20" % C, timeit(lambda: knn(xf, 20), iters=50, warm=5))
 
 
 if __name__ == "__main__":
