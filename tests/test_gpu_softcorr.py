@@ -51,6 +51,8 @@ def pipeline(request):
     (1, 8, 4, 4),           # tiny
     (2, 512, 1024, 1024),   # DCP shape (C3 per item)
     (1, 100, 131, 77),      # odd sizes: always the generic pipeline
+    (2, 40, 512, 256),      # CTA pairs with a K tail (40 = 2.5 x 16 channels, zero-filled by TMA)
+    (1, 72, 260, 516),      # CTA pair whose second member is mostly out of range, column tail
 ])
 def test_scores_and_correspondences_vs_fp64(pipeline, B, D, Ns, Nt):
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + D + Ns + Nt)
