@@ -36,7 +36,10 @@ enum KnnMode {
   MODE_DIRECT_FMA = 3      // key = -fma(dz,dz, fma(dx,dx, dy*dy))  (nvcc's contraction, see below)
 };
 
-constexpr int KNN_THREADS = 256;
+#ifndef L3D_KNN_THREADS
+#define L3D_KNN_THREADS 256  // 128 (4 CTAs/SM) and 512 measured in profiles/r01 (tune_knn.py)
+#endif
+constexpr int KNN_THREADS = L3D_KNN_THREADS;
 constexpr int KNN_WARPS = KNN_THREADS / 32;
 constexpr int KNN_TILE = 1024;   // candidates per tile = 32 lanes x 32 registers
 constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
