@@ -5,6 +5,7 @@
 #include "launch_count.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace l3d {
@@ -61,6 +62,27 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   const size_t out_bytes = (size_t)B * N * k * sizeof(int64_t);
   int rc = l3d::g_host.ensure(in_bytes, out_bytes);
   if (rc) return rc;
+  // Zero-copy output (L3D_KNN_HOST_ZEROCOPY=1, experiment): when idx_host is pinned, the kernel stores the
+  // indices straight into host memory over PCIe, so the write-back overlaps the whole kernel instead of
+  // following it.  Measured on the B200 box: see DESIGN.md §7 before enabling by default.
+  static int zero_copy = -1;
+  if (zero_copy < 0) {
+    const char* ev = getenv("L3D_KNN_HOST_ZEROCOPY");
+    zero_copy = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  if (zero_copy) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, idx_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        at.devicePointer) {
+      cudaStream_t s = l3d::g_host.stream;
+      cudaError_t ze = cudaMemcpyAsync(l3d::g_host.in, x_host, in_bytes, cudaMemcpyHostToDevice, s);
+      if (ze) return (int)ze;
+      rc = l3d_knn_expansion((const float*)l3d::g_host.in, B, N, k, (int64_t*)at.devicePointer, nullptr, s);
+      if (rc) return rc;
+      return (int)cudaStreamSynchronize(s);
+    }
+    cudaGetLastError();   // not a pinned buffer: fall through to the copy pipeline
+  }
   // The call is PCIe-bound: 8*k bytes of int64 indices return per 12 bytes of input.  The batch is
   // cut into slices that ping-pong over two streams so the device-to-host copy of slice i overlaps
   // the kernel of slice i+1 (clouds are independent; each slice is a whole number of clouds).
