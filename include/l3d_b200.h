@@ -62,6 +62,17 @@ int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
                       float* val_dev, void* stream);
 
 /*
+ * knn() + get_graph_feature() of utils/model_common_utils.py:3-9,132-155 in ONE launch for the xyz graph
+ * (C == 3): x_dev [B,3,N] -> idx_dev [B,N,k] int64 (required: autograd needs it) and
+ * feat_dev [B,6,N,k] = cat(x[:, :, idx], x[:, :, n] repeated k).  The neighbour coordinates are still in
+ * shared memory when a row's selection is final, so the separate gather launch and its re-read of the
+ * indices disappear (SURVEY.md §8d "kNN+graph-feature fused").  Same results, bit for bit, as
+ * l3d_knn_expansion followed by l3d_graph_feature.
+ */
+int l3d_knn_graph_feature(const float* x_dev, int B, int N, int k, int64_t* idx_dev, float* feat_dev,
+                          void* stream);
+
+/*
  * knn() of utils/model_common_utils.py:3-9 for any channel count C (the dynamic feature-space graphs of
  * PRNet's DGCNN, models/prnet.py:78-90: C = 64 / 64 / 128).  x_dev [B,C,N] -> idx_dev [B,N,k] int64.
  * Three launches on `stream`: |x_n|^2; the Gram matrix on the tensor cores (tcgen05, 3xTF32: fp32-class

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "l3d_debug_force_slow_path": [_I],
     "l3d_knn_expansion": [_P, _I, _I, _I, _P, _P, _P],
     "l3d_knn_expansion_host": [_P, _I, _I, _I, _P],
+    "l3d_knn_graph_feature": [_P, _I, _I, _I, _P, _P, _P],
     "l3d_knn_features_ws_bytes": [_I, _I, _I],
     "l3d_knn_features": [_P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_graph_feature": [_P, _P, _I, _I, _I, _I, _P, _P],

@@ -73,6 +73,7 @@ struct KnnParams {
   const float* query;  // [B,M,3] or nullptr when SELF
   void* out_idx;       // [B,M,k] int64 / int32
   float* out_val;      // optional [B,M,k]
+  float* feat_out;     // optional [B,6,N,k] graph feature (knn() on xyz only: SELF, [B,3,N] input)
   int B, N, M, k;
   int idx64;      // 1 -> int64 indices, 0 -> int32
   int val_xform;  // 0: key, 1: -key, 2: sqrt(-key)
@@ -605,6 +606,27 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
       const float* qp = p.query + row * 3;
       return knn_pack<MODE>(qp[0], qp[1], qp[2]);
     };
+    // get_graph_feature() fused into knn() (SURVEY.md §8d "a1+a2"): the neighbours' coordinates are still
+    // in shared memory when a row's indices are final, so cat(x[nbr], x[centre]) — [B,6,N,k] — is written
+    // here and the separate gather launch (and its re-read of 5.2 MB of indices) disappears.  The row's own
+    // warp re-reads the k indices it has just stored (L1) after a __syncwarp, so every selection path
+    // (network / whole-row sort / exact scan) is covered by one helper.
+    auto emit_feature = [&](long row) {
+      if (!(SELF && p.feat_out)) return;
+      __syncwarp();
+      const int n = (int)(row - (long)b * M);
+      const float4 ctr = packed[n];
+      const size_t cs = (size_t)N * p.k;
+      for (int pos = lane; pos < p.k; pos += 32) {
+        const long o = row * p.k + pos;
+        const int j = p.idx64 ? (int)reinterpret_cast<const volatile long long*>(p.out_idx)[o]
+                              : reinterpret_cast<const volatile int*>(p.out_idx)[o];
+        const float4 c = packed[j];
+        float* f = p.feat_out + ((size_t)b * 6 * N + n) * p.k + pos;
+        f[0] = c.x; f[cs] = c.y; f[2 * cs] = c.z;
+        f[3 * cs] = ctr.x; f[4 * cs] = ctr.y; f[5 * cs] = ctr.z;
+      }
+    };
     if (KS == 1 && !(p.full_sort && !p.force_slow)) {
       // KNN_R consecutive rows per warp; a ragged tail falls back to one row at a time
       unsigned long long* cb = reinterpret_cast<unsigned long long*>(cbuf);
@@ -614,16 +636,20 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
 #pragma unroll
         for (int r = 0; r < KNN_R; ++r) q[r] = load_query(row + r);
         knn_rows_v2<MODE, KNN_R>(p, packed, cb, q, row, ntiles, lane);
+#pragma unroll
+        for (int r = 0; r < KNN_R; ++r) emit_feature(row + r);
       }
       for (; row < seg_end; ++row) {
         const float4 q1[1] = {load_query(row)};
         knn_rows_v2<MODE, 1>(p, packed, cb, q1, row, ntiles, lane);
+        emit_feature(row);
       }
     } else {
       for (long row = seg + warp; row < seg_end; row += KNN_WARPS) {
         const float4 q = load_query(row);
         if (KS == 1) knn_row_sort<MODE>(p, packed, q, row, lane);
         else knn_row<MODE, KS>(p, packed, cbuf, q, row, ntiles, lane);
+        emit_feature(row);
       }
     }
     seg = seg_end;
@@ -736,6 +762,15 @@ extern "C" int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_
                                  float* val_dev, void* stream) {
   KnnParams p{};
   p.cand = x_dev; p.query = nullptr; p.out_idx = idx_dev; p.out_val = val_dev;
+  p.B = B; p.N = N; p.M = N; p.k = k; p.idx64 = 1; p.val_xform = 0;
+  return knn_launch<MODE_EXPANSION_NEG, true, true>(p, (cudaStream_t)stream);
+}
+
+extern "C" int l3d_knn_graph_feature(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
+                                     float* feat_dev, void* stream) {
+  if (!feat_dev) return L3D_ERR_INVALID;
+  KnnParams p{};
+  p.cand = x_dev; p.query = nullptr; p.out_idx = idx_dev; p.out_val = nullptr; p.feat_out = feat_dev;
   p.B = B; p.N = N; p.M = N; p.k = k; p.idx64 = 1; p.val_xform = 0;
   return knn_launch<MODE_EXPANSION_NEG, true, true>(p, (cudaStream_t)stream);
 }

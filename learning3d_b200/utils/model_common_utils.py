@@ -66,6 +66,36 @@ class _GraphFeature(torch.autograd.Function):
         return gx, None
 
 
+class _KnnGraphFeature(torch.autograd.Function):
+    """knn() + the gather of get_graph_feature in one kernel launch (xyz graph, C == 3): the neighbour
+    coordinates are read from the shared-memory copy of the cloud the selection just used.  Backward is the
+    same scatter as _GraphFeature (indices are saved; they carry no gradient, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        B, C, N = x.shape
+        idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+        out = torch.empty((B, 2 * C, N, k), dtype=torch.float32, device=x.device)
+        with _C.on_device(x.device):
+            _C.check(_C.lib().l3d_knn_graph_feature(_C.ptr(x), B, N, k, _C.ptr(idx), _C.ptr(out), _C.stream()),
+                     "get_graph_feature")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, N, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, C, N, k = ctx.dims
+        grad_out = grad_out.contiguous()
+        gx = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
+        with _C.on_device(grad_out.device):
+            _C.check(_C.lib().l3d_graph_feature_grad(_C.ptr(grad_out), _C.ptr(idx), B, C, N, k,
+                                                     _C.ptr(gx), _C.stream()),
+                     "get_graph_feature backward")
+        return gx, None
+
+
 def get_graph_feature(x, k=20, device=None):
     """utils/model_common_utils.py:132-155.  x [B,C,N(,1)] -> [B,2C,N,k] = cat(neighbour, centre).
 
@@ -74,6 +104,8 @@ def get_graph_feature(x, k=20, device=None):
     """
     x = x.view(*x.size()[:3])
     x = _C.require_cuda(x, "x")
+    if x.shape[1] == 3 and k <= x.shape[2]:
+        return _KnnGraphFeature.apply(x, k)          # one launch: selection + gather
     idx = knn(x, k=k)
     return _GraphFeature.apply(x, idx)
 

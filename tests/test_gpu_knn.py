@@ -218,3 +218,28 @@ def test_error_codes():
     assert knn(torch.rand(1, 64, 16, device=_dev()), 4).shape == (1, 16, 4)   # feature-space kNN (test_gpu_knn_features.py)
     rc = _C.lib().l3d_knn_expansion(_C.ptr(None), 1, 16, 4, _C.ptr(None), _C.ptr(None), _C.stream())
     assert rc == -1
+
+
+@pytest.mark.parametrize("B,N,k,slow", [(2, 1024, 20, 0), (2, 1024, 20, 1), (3, 200, 40, 0), (2, 2500, 24, 0),
+                                        (1, 333, 7, 0), (2, 64, 64, 0), (1, 1500, 100, 0)])
+def test_fused_knn_graph_feature_equals_knn_then_gather(B, N, k, slow):
+    """l3d_knn_graph_feature (one launch) == l3d_knn_expansion + l3d_graph_feature, bit for bit, on every
+    selection path (network, whole-row sort, KS > 1, exact scan)."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(B * 7 + N + k)
+    x = torch.rand(B, 3, N, device=dev, generator=g)
+    idx_a = torch.empty(B, N, k, dtype=torch.int64, device=dev)
+    feat_a = torch.empty(B, 6, N, k, device=dev)
+    idx_b = torch.empty_like(idx_a)
+    feat_b = torch.full_like(feat_a, float("nan"))
+    lib.l3d_debug_force_slow_path(slow)
+    try:
+        _C.check(lib.l3d_knn_expansion(_C.ptr(x), B, N, k, _C.ptr(idx_a), _C.ptr(None), _C.stream()))
+        _C.check(lib.l3d_graph_feature(_C.ptr(x), _C.ptr(idx_a), B, 3, N, k, _C.ptr(feat_a), _C.stream()))
+        _C.check(lib.l3d_knn_graph_feature(_C.ptr(x), B, N, k, _C.ptr(idx_b), _C.ptr(feat_b), _C.stream()))
+    finally:
+        lib.l3d_debug_force_slow_path(0)
+    assert torch.equal(idx_a, idx_b)
+    assert torch.equal(feat_a, feat_b)
