@@ -524,7 +524,7 @@ __host__ __device__ inline size_t knn_smem_bytes(int N, int KS) {
   return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad + (size_t)KNN_WARPS * KNN_CBUF(KS) * 8;
 }
 
-template <int MODE, int KS, bool SELF, bool CAND_BCN>
+template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false>
 __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -612,7 +612,7 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
     // warp re-reads the k indices it has just stored (L1) after a __syncwarp, so every selection path
     // (network / whole-row sort / exact scan) is covered by one helper.
     auto emit_feature = [&](long row) {
-      if (!(SELF && p.feat_out)) return;
+      if (!(FEAT && SELF)) return;   // compile-time: the plain knn() kernel carries none of this
       __syncwarp();
       const int n = (int)(row - (long)b * M);
       const float4 ctr = packed[n];
@@ -672,9 +672,9 @@ static int sm_count() {
   return n;
 }
 
-template <int MODE, int KS, bool SELF, bool CAND_BCN>
+template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false>
 static int knn_launch_t(KnnParams p, cudaStream_t stream) {
-  auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN>;
+  auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN, FEAT>;
   const size_t smem = knn_smem_bytes(p.N, KS);
   // the function attribute and the occupancy query are host-side driver calls (~5 us together):
   // cache them per (instantiation, device, smem size) so that a steady-state call is just the launch
@@ -739,10 +739,13 @@ static int knn_launch(KnnParams p, cudaStream_t stream) {
 #endif
   // Heavy selections out of a small cloud (FlowNet3D's flow embedding: k = 64 of N = 256) sort the
   // whole row instead of thresholding it.
-  if (p.N <= KNN_SORT_MAX_N && p.k * 8 >= p.N) {
-    p.full_sort = 1;
-    return knn_launch_t<MODE, 1, SELF, CAND_BCN>(p, stream);
+  if (p.N <= KNN_SORT_MAX_N && p.k * 8 >= p.N) p.full_sort = 1;
+  if (SELF && CAND_BCN && MODE == MODE_EXPANSION_NEG && p.feat_out) {   // fused get_graph_feature variant
+    if (p.full_sort || p.k <= 24) return knn_launch_t<MODE, 1, SELF, CAND_BCN, SELF && CAND_BCN>(p, stream);
+    if (p.k <= 48) return knn_launch_t<MODE, 2, SELF, CAND_BCN, SELF && CAND_BCN>(p, stream);
+    return knn_launch_t<MODE, 4, SELF, CAND_BCN, SELF && CAND_BCN>(p, stream);
   }
+  if (p.full_sort) return knn_launch_t<MODE, 1, SELF, CAND_BCN>(p, stream);
   // KS sets the number of lane groups (32*KS) whose maxima bound the k-th best key; the expected
   // number of survivors stays below the 64*KS-entry buffer while k <= ~0.75 * 32 * KS
   // (N = 1024: k = 24 -> 43, k = 48 -> 85, k = 100 -> ~170 survivors).  Larger k / N ratios still
