@@ -43,6 +43,33 @@ def test_product_refuses_cpu_tensors():
         knn(torch.rand(1, 3, 32), 4)
 
 
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Argument checks of the tensor-core entry points run before any CUDA call: exercised here on CPU."""
+    from learning3d_b200 import _C
+    import pytest
+    import torch
+    lib = _C.lib()
+    null = _C.ptr(None)
+    assert lib.l3d_soft_correspondence(null, null, null, 0, 8, 4, 4, null, null) == 0        # B == 0: nothing to do
+    assert lib.l3d_soft_correspondence(null, null, null, 1, 8, 4, 4, null, null) == -1       # null pointers
+    assert lib.l3d_soft_correspondence(null, null, null, -1, 8, 4, 4, null, null) == -1
+    assert lib.l3d_knn_features(null, 0, 64, 16, 4, null, null, null) == 0
+    assert lib.l3d_knn_features(null, 1, 64, 16, 4, null, null, null) == -1
+    assert lib.l3d_knn_features(null, 1, 0, 16, 4, null, null, null) == -1                     # C < 1
+    assert lib.l3d_knn_features_ws_bytes(2, 64, 100) >= 2 * 100 * 100 * 4 + 2 * 100 * 4
+    assert lib.l3d_knn_features_ws_bytes(0, 64, 100) == 0
+    assert lib.l3d_knn_graph_feature(null, 1, 16, 4, null, null, null) == -1                   # feat_dev missing
+    from learning3d_b200.utils import get_graph_feature
+    from learning3d_b200.utils.svd import soft_correspondence, SVDHead
+    with pytest.raises(RuntimeError, match="CUDA"):
+        soft_correspondence(torch.rand(1, 8, 4), torch.rand(1, 8, 4), torch.rand(1, 3, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        get_graph_feature(torch.rand(1, 64, 32), 4)                                           # feature-space graph
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            SVDHead(8, input_shape="bnc")(torch.rand(1, 8, 4), torch.rand(1, 8, 4), torch.rand(1, 4, 3), torch.rand(1, 4, 3))
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "learning3d_b200")
     for dirpath, _, files in os.walk(pkg):
