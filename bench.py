@@ -381,6 +381,15 @@ def tensor_core_bench(torch, dev, iters=30):
         out[name + "_us"] = ms * 1e3
         if flop:
             out[name + "_fp32_equiv_tflops"] = flop / (ms * 1e-3) / 1e12
+            # tensor-pipe view: 3xTF32 issues three TF32 MMAs per fp32-equivalent product; the TF32 peak is
+            # taken as half of the measured dense bf16 cuBLAS throughput (MEASURED_PEAKS.json)
+            issued = 3.0 * flop / (ms * 1e-3) / 1e12
+            out[name + "_issued_tf32_tflops"] = issued
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    out[name + "_frac_of_measured_tf32_peak"] = issued / (float(json.load(f)["bf16_tflops"]) / 2.0)
+            except Exception:
+                pass
     return out
 
 
