@@ -314,6 +314,10 @@ int l3d_soft_correspondence_status(void);
  *   0 = automatic (TMA + CTA pairs when eligible: Ns, Nt multiples of 4, 16-byte aligned embeddings, Ns > 128),
  *   1 = force the generic (LDG producer, any shape) pipeline,  2 = TMA pipeline without CTA pairs. */
 void l3d_debug_soft_correspondence_force_generic(int on);
+/* Testing hook for the target-range split of l3d_soft_correspondence / l3d_knn_features (small batches
+ * spread one row block's target tiles over several CTAs and merge the partial softmax states):
+ * -1 = never split, 0 = automatic, n > 0 = force n splits. */
+void l3d_debug_soft_correspondence_split(int n);
 /* Debug aid: shared-memory image (4 x 4096 floats: A_hi, A_lo, B_hi, B_lo) of the first pipeline stage of
  * CTA (0,0) in the last l3d_debug_soft_correspondence_scores launch on the TMA path -> host_out. */
 int l3d_debug_soft_correspondence_tiles(float* host_out);

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "l3d_soft_correspondence": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_soft_correspondence_status": [],
     "l3d_debug_soft_correspondence_force_generic": [_I],
+    "l3d_debug_soft_correspondence_split": [_I],
     "l3d_debug_soft_correspondence_tiles": [_P],
     "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -71,6 +72,7 @@ _RESTYPE = {
     "l3d_launch_count": ctypes.c_uint64,
     "l3d_debug_force_slow_path": None,
     "l3d_debug_soft_correspondence_force_generic": None,
+    "l3d_debug_soft_correspondence_split": None,
     "l3d_chamfer_ws_bytes": ctypes.c_size_t,
     "l3d_knn_features_ws_bytes": ctypes.c_size_t,
     "l3d_emd_forward_ws_bytes": ctypes.c_size_t,

@@ -77,6 +77,8 @@ struct SoftCorrParams {
   const float* xx_b;      // [B, Nt]
   float* keys;            // [B, Ns, Nt]   ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2
   int* err;               // device error word (0 = ok)
+  float* part;            // split target range only: partial softmax states [B, Ns, gridDim.z, 8]
+  int tiles_per_split;    // target tiles handled by one CTA (all of them when gridDim.z == 1)
   int B, D, Ns, Nt;
   float c;                // log2(e) / sqrt(D)
 };
@@ -311,7 +313,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * SC_BM;
-  const int num_jb = (p.Nt + SC_BN - 1) / SC_BN;
+  // target tiles of this CTA: blockIdx.z selects a contiguous group of p.tiles_per_split tiles (small
+  // batches split the target range over several CTAs / clusters so that the whole GPU is used; each
+  // group leaves a partial softmax state that softcorr_merge_kernel combines).  jb below is LOCAL.
+  const int jb0 = (int)blockIdx.z * p.tiles_per_split;
+  const int num_jb = min(p.tiles_per_split, (p.Nt + SC_BN - 1) / SC_BN - jb0);
   const int num_kb = (p.D + SC_BK - 1) / SC_BK;
   const int total = num_jb * num_kb;
 
@@ -356,7 +362,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     bool ok = true;
     for (int jb = 0; jb < num_jb; ++jb) {
       const int a = jb & 1;
-      const int j0 = jb * SC_BN;
+      const int j0 = (jb0 + jb) * SC_BN;
 #pragma unroll
       for (int jj = tid; jj < SC_BN; jj += SC_EPI_THREADS) {
         const int j = j0 + jj;
@@ -451,7 +457,12 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       }
     }
     if (!ok) atomicCAS(p.err, 0, 1);
-    if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns) {
+    if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns && p.part) {
+      // split target range: leave (running max in log2 units, sum, sum*xyz) for the merge kernel
+      float* q = p.part + (((size_t)b * p.Ns + i) * gridDim.z + blockIdx.z) * 8;
+      *reinterpret_cast<float4*>(q) = make_float4(m, l, ax, ay);
+      q[4] = az;
+    } else if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns) {
       const float inv = __fdividef(1.f, l);
       float* o = p.out + (size_t)b * 3 * p.Ns + i;
       o[0] = __fmul_rn(ax, inv);
@@ -502,7 +513,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       for (int it = 0; it < total; ++it) {
         const int jb = it / num_kb, kb = it - jb * num_kb;
         sc_load_row(A, p.D, p.Ns, kb * SC_BK, i0 + r, va);
-        sc_load_row(Bm, p.D, p.Nt, kb * SC_BK, jb * SC_BN + r, vb);
+        sc_load_row(Bm, p.D, p.Nt, kb * SC_BK, (jb0 + jb) * SC_BN + r, vb);
         const int s = it % SC_STAGES;
         const uint32_t n = (uint32_t)(it / SC_STAGES);
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
@@ -583,7 +594,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         // a pair member fetches only its half of the 256 target columns
 #pragma unroll
         for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
-          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, jb * SC_BN + (int)crank * Cfg::BN_LOCAL + 32 * q,
+          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, (jb0 + jb) * SC_BN + (int)crank * Cfg::BN_LOCAL + 32 * q,
                       kb * SC_BK, b, &sh->tma_full[s]);
       }
       __syncwarp();
@@ -646,6 +657,30 @@ using namespace l3d;
 
 static int g_softcorr_force_generic = 0;
 
+// -1: never split the target range, 0: automatic (small batches), > 0: forced number of splits (testing hook)
+static int g_softcorr_split = 0;
+
+// Combines the partial softmax states of a split target range: state z = (m_z in log2 units, l_z, a_z[3]);
+// out = sum_z a_z 2^(m_z - M) / sum_z l_z 2^(m_z - M), M = max_z m_z.
+static __global__ void softcorr_merge_kernel(const float* __restrict__ part, int B, int Ns, int nsplit,
+                                             float* __restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * Ns) return;
+  const float* q = part + (size_t)t * nsplit * 8;
+  float M = -INFINITY;
+  for (int z = 0; z < nsplit; ++z) M = fmaxf(M, q[z * 8]);
+  float l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+  for (int z = 0; z < nsplit; ++z) {
+    const float w = ex2_approx(__fsub_rn(q[z * 8], M));
+    l = fmaf(w, q[z * 8 + 1], l);
+    ax = fmaf(w, q[z * 8 + 2], ax); ay = fmaf(w, q[z * 8 + 3], ay); az = fmaf(w, q[z * 8 + 4], az);
+  }
+  const int b = (int)(t / Ns), i = (int)(t - (long)b * Ns);
+  const float inv = __fdividef(1.f, l);
+  float* o = out + (size_t)b * 3 * Ns + i;
+  o[0] = __fmul_rn(ax, inv); o[Ns] = __fmul_rn(ay, inv); o[2 * (size_t)Ns] = __fmul_rn(az, inv);
+}
+
 // Launches the GEMM pipeline with epilogue EPI on an already filled parameter block (src_emb, tgt_emb,
 // B, D, Ns, Nt and the epilogue's own pointers).
 template <int EPI>
@@ -679,11 +714,35 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
   if (tma) tma = make_emb_tmap(&ma, p.src_emb, p.B, p.D, p.Ns) && make_emb_tmap(&mb, p.tgt_emb, p.B, p.D, p.Nt);
-  if (tma && g_softcorr_force_generic != 2 && p.Ns > SC_BM) {
+  const bool pair = tma && g_softcorr_force_generic != 2 && p.Ns > SC_BM;
+
+  // Small batches: with one CTA (pair) per 128 (256) source rows a B = 2 call would occupy 8 of 74 TPCs.
+  // Split the target tiles over gridDim.z so that about one wave of CTAs exists; each split leaves a
+  // partial softmax state per row (EPI_SOFTMAX_XYZ), combined by softcorr_merge_kernel.
+  const int bn = tma ? SoftCorrCfg<true>::BN : SoftCorrCfg<false>::BN;
+  const int tiles = (p.Nt + bn - 1) / bn;
+  const long units = pair ? (long)((p.Ns + 2 * SC_BM - 1) / (2 * SC_BM)) * p.B : (long)grid.x * p.B;
+  const long slots = pair ? 74 : 148;
+  int jsplit = 1;
+  if (g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
+    jsplit = (int)((slots + units - 1) / units);
+    if (g_softcorr_split > 0) jsplit = g_softcorr_split;
+    if (jsplit > tiles) jsplit = tiles;
+  }
+  p.tiles_per_split = (tiles + jsplit - 1) / jsplit;
+  jsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;     // no empty split
+  p.part = nullptr;
+  if (EPI == EPI_SOFTMAX_XYZ && jsplit > 1) {
+    cudaError_t me = cudaMallocAsync((void**)&p.part, (size_t)p.B * p.Ns * jsplit * 8 * sizeof(float),
+                                     (cudaStream_t)stream);
+    if (me != cudaSuccess) return (int)me;
+  }
+  grid.z = jsplit;
+  if (pair) {
     // CTA pairs: cluster (2,1,1), two adjacent 128-row blocks of one batch item (an odd last block gets an
     // all-out-of-range partner: TMA zero-fills its tiles and its epilogue stores nothing)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * ((p.Ns + 2 * SC_BM - 1) / (2 * SC_BM)), p.B);
+    cfg.gridDim = dim3(2 * ((p.Ns + 2 * SC_BM - 1) / (2 * SC_BM)), p.B, jsplit);
     cfg.blockDim = dim3(SC_THREADS);
     cfg.dynamicSmemBytes = smem_p;
     cfg.stream = (cudaStream_t)stream;
@@ -699,6 +758,15 @@ static int sc_launch(SoftCorrParams p, void* stream) {
     softcorr_kernel<false, EPI><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);
   count_launch();
   L3D_LAUNCH_CHECK();
+  if (p.part) {
+    const long rows = (long)p.B * p.Ns;
+    softcorr_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.B, p.Ns,
+                                                                                            jsplit, p.out);
+    count_launch();
+    cudaError_t fe = cudaFreeAsync(p.part, (cudaStream_t)stream);
+    L3D_LAUNCH_CHECK();
+    if (fe != cudaSuccess) return (int)fe;
+  }
   return L3D_OK;
 }
 
@@ -797,6 +865,9 @@ extern "C" int l3d_debug_soft_correspondence_tiles(float* host_out) {
 
 // Testing hook: nonzero forces the generic (LDG producer) operand pipeline even for TMA-eligible shapes.
 extern "C" void l3d_debug_soft_correspondence_force_generic(int on) { g_softcorr_force_generic = on; }
+
+// Testing hook: -1 = never split the target range over CTAs, 0 = automatic, n > 0 = force n splits.
+extern "C" void l3d_debug_soft_correspondence_split(int n) { g_softcorr_split = n; }
 
 // Synchronises the device and returns the pipeline error word of l3d_soft_correspondence
 // (0 = ok; 1/2/3/4 = an epilogue / producer / MMA-issuer / TMA-issuer wait ran out).  Test and debug aid.

@@ -103,3 +103,18 @@ def test_graph_feature_on_features_and_add_one_to_k():
     assert feat.shape == (2, 128, 256, 20)
     nbr = torch.gather(x.unsqueeze(2).expand(-1, -1, 256, -1), 3, idx.unsqueeze(1).expand(-1, 64, -1, -1))
     assert torch.equal(feat[:, :64], nbr) and torch.equal(feat[:, 64:], x.unsqueeze(3).expand(-1, -1, -1, 20))
+
+
+@pytest.mark.parametrize("split", [2, 4])
+def test_feature_knn_with_split_target_range(split):
+    from learning3d_b200 import _C
+    from learning3d_b200.utils import knn
+    g = torch.Generator(device=DEV).manual_seed(50 + split)
+    x = torch.randn(1, 64, 1024, device=DEV, generator=g)
+    _C.lib().l3d_debug_soft_correspondence_split(split)
+    try:
+        idx = knn(x, 20)
+    finally:
+        _C.lib().l3d_debug_soft_correspondence_split(0)
+    _check(x, 20, idx)
+    assert torch.equal(idx, knn(x, 20))      # automatic split (B = 1) gives the same keys, hence the same graph

@@ -132,3 +132,25 @@ def test_svd_head_inference_path_matches_reference_ops():
     R2, t2 = head(emb_g, emb_t, src, tgt)
     assert (R1 - R2).abs().max().item() <= 2e-5 and (t1 - t2).abs().max().item() <= 2e-5
     assert (R1 - Rz).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("split", [0, 2, 3, 4, -1])
+@pytest.mark.parametrize("B,D,Ns,Nt", [(1, 64, 128, 1024), (2, 512, 1024, 1024), (1, 96, 260, 1300)])
+def test_target_range_split_and_merge(pipeline, split, B, D, Ns, Nt):
+    """Small batches spread the target tiles of a row block over several CTAs (gridDim.z) and merge the
+    partial softmax states: same result as the unsplit kernel, for automatic and forced split counts."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    g = torch.Generator(device=DEV).manual_seed(100 + split + B + Ns + Nt)
+    a = torch.randn(B, D, Ns, device=DEV, generator=g)
+    b = torch.randn(B, D, Nt, device=DEV, generator=g)
+    t = torch.rand(B, 3, Nt, device=DEV, generator=g) * 2 - 1
+    lib.l3d_debug_soft_correspondence_split(split)
+    try:
+        out, sc = _run_debug(a, b, t)
+    finally:
+        lib.l3d_debug_soft_correspondence_split(0)
+    s_ref, o_ref, bound = _ref(a, b, t)
+    assert not torch.isnan(out).any() and not torch.isnan(sc).any()
+    assert ((sc.double() - s_ref).abs() <= 4e-6 * bound + 1e-30).all()
+    assert (out.double() - o_ref).abs().max().item() <= 2e-5, (pipeline, split)
