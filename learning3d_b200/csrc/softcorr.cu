@@ -733,6 +733,17 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   jsplit = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;     // no empty split
   p.part = nullptr;
   if (EPI == EPI_SOFTMAX_XYZ && jsplit > 1) {
+    // stream-ordered scratch from the device's default pool; keep freed blocks cached in the pool (the
+    // default release threshold of 0 hands them back to the driver at every sync: ~100 us per call)
+    static thread_local int pool_dev = -1;
+    if (pool_dev != dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_dev = dev;
+    }
     cudaError_t me = cudaMallocAsync((void**)&p.part, (size_t)p.B * p.Ns * jsplit * 8 * sizeof(float),
                                      (cudaStream_t)stream);
     if (me != cudaSuccess) return (int)me;
