@@ -722,7 +722,13 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   const int bn = tma ? SoftCorrCfg<true>::BN : SoftCorrCfg<false>::BN;
   const int tiles = (p.Nt + bn - 1) / bn;
   const long units = pair ? (long)((p.Ns + 2 * SC_BM - 1) / (2 * SC_BM)) * p.B : (long)grid.x * p.B;
-  const long slots = pair ? 74 : 148;
+  static thread_local int sm_dev = -1, sm_count = 148;
+  if (sm_dev != dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sm_count = n;
+    sm_dev = dev;
+  }
+  const long slots = pair ? sm_count / 2 : sm_count;   // 1 CTA per SM; a pair needs both SMs of a TPC
   int jsplit = 1;
   if (g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
     jsplit = (int)((slots + units - 1) / units);
