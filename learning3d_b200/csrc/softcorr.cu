@@ -768,13 +768,22 @@ static int sc_launch(SoftCorrParams p, void* stream) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, softcorr_kernel<true, EPI, 2>, p, ma, mb);
-    if (le != cudaSuccess) return (int)le;
+    if (le != cudaSuccess) {
+      if (p.part) cudaFreeAsync(p.part, (cudaStream_t)stream);
+      return (int)le;
+    }
   } else if (tma)
     softcorr_kernel<true, EPI><<<grid, SC_THREADS, smem_t, (cudaStream_t)stream>>>(p, ma, mb);
   else
     softcorr_kernel<false, EPI><<<grid, SC_THREADS, smem_g, (cudaStream_t)stream>>>(p, ma, mb);
   count_launch();
-  L3D_LAUNCH_CHECK();
+  {
+    const cudaError_t le2 = cudaGetLastError();
+    if (le2 != cudaSuccess) {
+      if (p.part) cudaFreeAsync(p.part, (cudaStream_t)stream);   // do not leak the scratch on a failed launch
+      return (int)le2;
+    }
+  }
   if (p.part) {
     const long rows = (long)p.B * p.Ns;
     softcorr_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.B, p.Ns,
