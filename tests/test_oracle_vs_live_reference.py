@@ -65,3 +65,33 @@ def test_grouping_functions_live(oracle_mod, ref, seed):
     same = oi2 == kidx.numpy()
     assert same.mean() > 0.99                       # exact distance ties may order differently
     np.testing.assert_allclose(ov[same], val.numpy()[same], rtol=2e-7, atol=1e-7)
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, "utils", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_pointconv_and_ppfnet_variants_live(oracle_mod, seed):
+    pcu, ppf = _load("pointconv_util"), _load("ppfnet_util")
+    rng = np.random.default_rng(900 + seed)
+    B, N, S = 2, int(rng.integers(64, 200)), int(rng.integers(8, 32))
+    xyz = rng.random((B, N, 3), dtype=np.float32)
+    new_xyz = np.ascontiguousarray(xyz[:, :S])
+    t_xyz, t_new = torch.from_numpy(xyz), torch.from_numpy(new_xyz)
+    # pointconv knn_point: topk(sorted=False) -> compare as sets per row (pointconv_util.py:107-118)
+    ns = int(rng.integers(2, 16))
+    want = np.sort(pcu.knn_point(ns, t_xyz, t_new).numpy(), axis=-1)
+    got = np.sort(oracle_mod.knn_sqdist(xyz, new_xyz, ns), axis=-1)
+    assert (want == got).mean() > 0.995
+    # start-0 FPS (pointconv_util.py:60-83) and density (:199-209)
+    assert np.array_equal(og.farthest_point_sample(xyz, S), pcu.farthest_point_sample(t_xyz, S).numpy())
+    np.testing.assert_allclose(og.compute_density(xyz, 0.2), pcu.compute_density(t_xyz, 0.2).numpy(), rtol=2e-6)
+    # ppfnet ball query with the query's own index masked out (ppfnet_util.py:96-131)
+    itself = torch.arange(S).view(1, S).repeat(B, 1)
+    want = ppf.query_ball_point(0.3, 12, t_xyz, t_new, itself).numpy()
+    got = og.query_ball_point(0.3, 12, xyz, new_xyz, itself=itself.numpy())
+    assert np.array_equal(want, got)
