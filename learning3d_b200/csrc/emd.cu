@@ -49,6 +49,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// __expf(level * d2) exactly as nvcc expands it in the reference kernels (emd.cuh:58,103,157; SASS of
+// oracle/_ref/libemd_ref.so): FMUL level*d2, FMUL by fp32 log2(e), MUFU.EX2.  (Below 2^-126 the reference
+// squares ex2(t/2) to keep denormals; those weights are < 1.2e-38 and flush to 0 here.)
+__device__ __forceinline__ float emd_exp(float level, float d2) {
+  return ex2_approx(__fmul_rn(__fmul_rn(level, d2), LOG2E));
+}
+
 __device__ __forceinline__ float emd_d2(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = bx - ax, dy = by - ay, dz = bz - az;
   return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
@@ -61,7 +68,7 @@ struct EmdSweepParams {
   const float* cols;    // [B,nc,3] column cloud
   int B, nr, nc;
   int phase;
-  float lvlA, lvlB;     // level*log2(e) for sweep A (and B when fused)
+  float lvlA, lvlB;     // level (-4^j) of sweep A (and B when fused)
   const float* vA;      // [B,nc] column weights of sweep A
   const float* vB;      // [B,nc] column weights of sweep B (fused only)
   // per-row state (all [B,nr])
@@ -104,8 +111,8 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(const EmdSweepPa
 #pragma unroll
       for (int i = 0; i < EMD_R; ++i) {
         const float d2 = emd_d2(rx[i], ry[i], rz[i], q.x, q.y, q.z);
-        sa[i] = fmaf(ex2_approx(p.lvlA * d2), q.w, sa[i]);
-        if (FUSED) sb[i] = fmaf(ex2_approx(p.lvlB * d2), vb, sb[i]);
+        sa[i] = fmaf(emd_exp(p.lvlA, d2), q.w, sa[i]);
+        if (FUSED) sb[i] = fmaf(emd_exp(p.lvlB, d2), vb, sb[i]);
       }
     }
   }
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_final_kernel(const EmdFinalPa
       float mt = 0.f;
 #pragma unroll
       for (int j = 0; j < EMD_LEVELS; ++j) {
-        const float e = (j == EMD_LEVELS - 1) ? 1.0f : ex2_approx(p.lvl[j] * d2);
+        const float e = (j == EMD_LEVELS - 1) ? 1.0f : emd_exp(p.lvl[j], d2);
         const float rl = p.ratioL[((size_t)j * p.B + b) * p.n + k];
         mt += e * rl * rr[j];                                       // match += w   (emd.cuh:157-158)
       }
@@ -342,7 +349,7 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
   const dim3 gridL((n + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
   const dim3 gridR((m + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
   EmdFinalParams fp{};
-  for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it) * LOG2E;
+  for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it);
 
   for (int it = 0; it < EMD_LEVELS; ++it) {
     if (it == 0) {

@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(256) index_points_kernel(const float* __restri
     const long r = t / C;
     const int c = (int)(t - r * C);
     const long j = idx[(size_t)b * R + r];
-    out[(size_t)b * total + t] = __ldg(points + ((size_t)b * N + j) * C + c);
+    // an index outside [0, N) (torch-mode ball query pads empty rows with N, model_common_utils.py:116) would
+    // be a device-side assert in the reference's advanced indexing; here it reads nothing and yields NaN
+    out[(size_t)b * total + t] = ((unsigned long)j < (unsigned long)N)
+                                     ? __ldg(points + ((size_t)b * N + j) * C + c) : __int_as_float(0x7fc00000);
   }
 }
 __global__ void __launch_bounds__(256) index_points_grad_kernel(const float* __restrict__ grad_out,
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(256) index_points_grad_kernel(const float* __r
     const long r = t / C;
     const int c = (int)(t - r * C);
     const long j = idx[(size_t)b * R + r];
-    atomicAdd(grad_points + ((size_t)b * N + j) * C + c, grad_out[(size_t)b * total + t]);
+    if ((unsigned long)j < (unsigned long)N)   // out-of-range rows received NaN in the forward; scatter nothing
+      atomicAdd(grad_points + ((size_t)b * N + j) * C + c, grad_out[(size_t)b * total + t]);
   }
 }
 

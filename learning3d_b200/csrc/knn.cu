@@ -26,8 +26,11 @@
 #include "launch_count.h"
 
 #include <math.h>
+#include <mutex>
 
 namespace l3d {
+
+constexpr size_t KNN_SMEM_LIMIT = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 
 enum KnnMode {
   MODE_EXPANSION_NEG = 0,  // key = ((-|c|^2) + 2 q.c) - |q|^2              (largest = nearest)
@@ -115,6 +118,40 @@ __device__ __forceinline__ float4 knn_pack(float x, float y, float z) {
     w = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));  // sum(x**2)
   return make_float4(x, y, z, w);
 }
+
+// ---- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): two independent IEEE fp32 lanes per instruction, each
+// rounded exactly like the scalar op, so a key computed in a packed lane is bit-identical to knn_key<>.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+#ifndef L3D_KNN_F32X2
+#define L3D_KNN_F32X2 1      // expansion-mode k <= 24 path: evaluate two candidates per FFMA2 (pair layout below)
+#endif
+// Pair layout of a candidate tile for the packed path: lane l's candidates e and e+1 (e even) of tile t, i.e.
+// points j = t*1024 + e*32 + l and j + 32, sit side by side so that one LDS.128 feeds two FFMA2 operands:
+//   pair_xy[t*512 + (e/2)*32 + l] = (x_e, x_e+1, y_e, y_e+1),  pair_zw[..] = (z_e, z_e+1, -|c_e|^2, -|c_e+1|^2)
+template <int MODE, int KS>
+struct KnnPairs { static constexpr bool value = (L3D_KNN_F32X2 != 0) && (L3D_KNN_DEFER_QW != 0) && MODE == MODE_EXPANSION_NEG && KS == 1; };
 
 template <int MODE>
 __device__ __forceinline__ float4 knn_padding() {
@@ -390,10 +427,12 @@ __device__ __forceinline__ void knn_row_v2(const KnnParams& p, const float4* __r
 // for R queries.  The second ncu capture showed the shared-memory/shuffle (MIO) pipe at 74 % with
 // 128 of ~220 wavefronts per row being candidate loads: R = 2 halves them and doubles the ILP of
 // the (shuffle-latency-bound) sorting networks.
-template <int MODE, int R>
+template <int MODE, int R, bool PAIRS = false>
 __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __restrict__ packed,
                                             unsigned long long* __restrict__ cbuf, const float4 (&q)[R],
-                                            long row0, int ntiles, int lane) {
+                                            long row0, int ntiles, int lane,
+                                            const ulonglong2* __restrict__ pair_xy = nullptr,
+                                            const ulonglong2* __restrict__ pair_zw = nullptr) {
   constexpr int CAP = 64;
   const int k = p.k;
   int base[R];
@@ -410,14 +449,33 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
     // threshold is lowered to cover every s that can round to the k-th key (thr computation below).
     constexpr bool DEFER = (L3D_KNN_DEFER_QW != 0) && MODE == MODE_EXPANSION_NEG;
     float d[R][32];
-    const float4* pt = packed + t * KNN_TILE + lane;
+    if constexpr (PAIRS) {
+      // two candidates per instruction: s = fma(2, fma(qz,cz, fma(qy,cy, qx*cx)), -|c|^2), same op order per lane
+      const ulonglong2* pxy = pair_xy + t * (KNN_TILE / 2) + lane;
+      const ulonglong2* pzw = pair_zw + t * (KNN_TILE / 2) + lane;
+      unsigned long long qx2[R], qy2[R], qz2[R];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const float4 c = pt[e * 32];
+      for (int r = 0; r < R; ++r) { qx2[r] = f2_pack(q[r].x, q[r].x); qy2[r] = f2_pack(q[r].y, q[r].y); qz2[r] = f2_pack(q[r].z, q[r].z); }
+      const unsigned long long two2 = f2_pack(2.0f, 2.0f);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (DEFER) d[r][e] = fmaf(2.0f, fmaf(q[r].z, c.z, fmaf(q[r].y, c.y, __fmul_rn(q[r].x, c.x))), -c.w);
-        else d[r][e] = knn_key<MODE>(q[r], c);
+      for (int pe = 0; pe < 16; ++pe) {
+        const ulonglong2 a = pxy[pe * 32], bz = pzw[pe * 32];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long dot = f2_fma(qz2[r], bz.x, f2_fma(qy2[r], a.y, f2_mul(qx2[r], a.x)));
+          f2_unpack(f2_fma(two2, dot, bz.y), d[r][2 * pe], d[r][2 * pe + 1]);
+        }
+      }
+    } else {
+      const float4* pt = packed + t * KNN_TILE + lane;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float4 c = pt[e * 32];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (DEFER) d[r][e] = fmaf(2.0f, fmaf(q[r].z, c.z, fmaf(q[r].y, c.y, __fmul_rn(q[r].x, c.x))), -c.w);
+          else d[r][e] = knn_key<MODE>(q[r], c);
+        }
       }
     }
     float mx[R];
@@ -447,9 +505,20 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
       // differences with a clear sign bit; one FADD (FMA pipe) + one funnel shift (ALU pipe) per key
       // instead of FSETP + predicated OR (two ALU-pipe instructions; the ALU pipe is the busier one).
       uint32_t neg = 0u;
+      if constexpr (PAIRS) {
+        const unsigned long long nthr = f2_pack(-thr, -thr);
 #pragma unroll
-      for (int e = 31; e >= 0; --e)
-        neg = __funnelshift_l(__float_as_uint(__fsub_rn(d[r][e], thr)), neg, 1);
+        for (int pe = 15; pe >= 0; --pe) {
+          float s0, s1;
+          f2_unpack(f2_add(f2_pack(d[r][2 * pe], d[r][2 * pe + 1]), nthr), s0, s1);
+          neg = __funnelshift_l(__float_as_uint(s1), neg, 1);
+          neg = __funnelshift_l(__float_as_uint(s0), neg, 1);
+        }
+      } else {
+#pragma unroll
+        for (int e = 31; e >= 0; --e)
+          neg = __funnelshift_l(__float_as_uint(__fsub_rn(d[r][e], thr)), neg, 1);
+      }
       const uint32_t mk = ~neg;
       mask[r] = mk;
       cnt[r] = __popc(mk);
@@ -516,15 +585,16 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
 //   [0,16)                       mbarrier
 //   [16, 16 + 12*KNN_CHUNK)      raw staging chunk (3 * KNN_CHUNK floats)
 //   [.., + 16*NPAD)              packed candidates (float4), NPAD = N rounded up to KNN_TILE
+//   [.., + 16*NPAD)              pair layout of the same candidates (packed-f32x2 path only, KnnPairs<>)
 //   [.., + KNN_WARPS*CAP*8)      per-warp survivor buffers
 // survivor-buffer entries per warp: KS = 1 runs KNN_R rows per warp, 64 entries each
 #define KNN_CBUF(KS) ((KS) == 1 ? 64 * KNN_R : 64 * (KS))
-__host__ __device__ inline size_t knn_smem_bytes(int N, int KS) {
+__host__ __device__ inline size_t knn_smem_bytes(int N, int KS, bool pairs) {
   const size_t npad = (size_t)((N + KNN_TILE - 1) / KNN_TILE) * KNN_TILE;
-  return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad + (size_t)KNN_WARPS * KNN_CBUF(KS) * 8;
+  return 16 + 12 * (size_t)KNN_CHUNK + 16 * npad * (pairs ? 2 : 1) + (size_t)KNN_WARPS * KNN_CBUF(KS) * 8;
 }
 
-template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false>
+template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false, bool PAIRS = false>
 __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -533,7 +603,10 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   const int N = p.N, M = p.M;
   const int ntiles = (N + KNN_TILE - 1) / KNN_TILE;
   const int npad = ntiles * KNN_TILE;
-  uint2* cbuf_all = reinterpret_cast<uint2*>(packed + npad);
+  static_assert(!PAIRS || KnnPairs<MODE, KS>::value, "the packed path exists for the k <= 24 expansion mode only");
+  ulonglong2* pair_xy = reinterpret_cast<ulonglong2*>(packed + npad);          // npad/2 entries each
+  ulonglong2* pair_zw = pair_xy + npad / 2;
+  uint2* cbuf_all = reinterpret_cast<uint2*>(packed + (PAIRS ? 2 : 1) * npad);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -599,6 +672,17 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
     }
     for (int i = N + tid; i < npad; i += KNN_THREADS) packed[i] = knn_padding<MODE>();
     __syncthreads();
+    if (PAIRS && !(p.full_sort && !p.force_slow)) {
+      // pair layout for the packed-f32x2 distance loop: thread = (tile, pair, lane); two conflict-free
+      // LDS.128 in, two STS.128 out
+      for (int i = tid; i < npad / 2; i += KNN_THREADS) {
+        const int t = i >> 9, pe = (i >> 5) & 15, l = i & 31;
+        const float4 c0 = packed[t * KNN_TILE + (2 * pe) * 32 + l], c1 = packed[t * KNN_TILE + (2 * pe + 1) * 32 + l];
+        pair_xy[i] = make_ulonglong2(f2_pack(c0.x, c1.x), f2_pack(c0.y, c1.y));
+        pair_zw[i] = make_ulonglong2(f2_pack(c0.z, c1.z), f2_pack(-c0.w, -c1.w));
+      }
+      __syncthreads();
+    }
 
     // ---- rows of this segment, one warp each ---------------------------------------
     auto load_query = [&](long row) -> float4 {
@@ -635,7 +719,7 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
         float4 q[KNN_R];
 #pragma unroll
         for (int r = 0; r < KNN_R; ++r) q[r] = load_query(row + r);
-        knn_rows_v2<MODE, KNN_R>(p, packed, cb, q, row, ntiles, lane);
+        knn_rows_v2<MODE, KNN_R, PAIRS>(p, packed, cb, q, row, ntiles, lane, pair_xy, pair_zw);
 #pragma unroll
         for (int r = 0; r < KNN_R; ++r) emit_feature(row + r);
       }
@@ -672,21 +756,37 @@ static int sm_count() {
   return n;
 }
 
-template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false>
+template <int MODE, int KS, bool SELF, bool CAND_BCN, bool FEAT = false, bool PAIRS = false>
 static int knn_launch_t(KnnParams p, cudaStream_t stream) {
-  auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN, FEAT>;
-  const size_t smem = knn_smem_bytes(p.N, KS);
-  // the function attribute and the occupancy query are host-side driver calls (~5 us together):
-  // cache them per (instantiation, device, smem size) so that a steady-state call is just the launch
-  static thread_local int c_dev = -1, c_occ = 0;
-  static thread_local size_t c_smem = 0;
+  if constexpr (!PAIRS && KnnPairs<MODE, KS>::value) {
+    // packed-f32x2 variant whenever its second copy of the cloud fits in shared memory (N <= 6144)
+    if (knn_smem_bytes(p.N, KS, true) <= KNN_SMEM_LIMIT)
+      return knn_launch_t<MODE, KS, SELF, CAND_BCN, FEAT, true>(p, stream);
+  }
+  auto kern = knn_kernel<MODE, KS, SELF, CAND_BCN, FEAT, PAIRS>;
+  const size_t smem = knn_smem_bytes(p.N, KS, PAIRS);
+  if (smem > KNN_SMEM_LIMIT) return L3D_ERR_UNSUPPORTED;
   int dev = 0;
   cudaGetDevice(&dev);
+  // The opt-in shared-memory limit is a per-(device, function) attribute shared by every host thread: raise it
+  // ONCE to the architectural maximum (never lower it), under a process-wide lock.  A per-call exact size
+  // would let a second thread with a smaller N lower it under a launch that still needs the larger one.
+  {
+    static std::mutex mu;
+    static uint64_t done_mask = 0;        // bit = device ordinal (ordinals >= 64 set the attribute every call)
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 64 || !(done_mask >> dev & 1)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM_LIMIT);
+      if (e != cudaSuccess) return (int)e;
+      if (dev < 64) done_mask |= (uint64_t)1 << dev;
+    }
+  }
+  // the occupancy query is a host-side driver call (~3 us): cache it per (thread, device, smem size)
+  static thread_local int c_dev = -1, c_occ = 0;
+  static thread_local size_t c_smem = 0;
   if (dev != c_dev || smem != c_smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     int o = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, KNN_THREADS, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, KNN_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     c_dev = dev; c_smem = smem; c_occ = o;
   }

@@ -456,7 +456,25 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         else mbar_arrive(&sh->acc_empty[a]);
       }
     }
-    if (!ok) atomicCAS(p.err, 0, 1);
+    if (!ok) {
+      // a timed-out pipeline must not look like a result: poison this row's outputs with NaN (R and t downstream
+      // become NaN) and raise the sticky error word for l3d_soft_correspondence_status()
+      atomicCAS(p.err, 0, 1);
+      const float qnan = __int_as_float(0x7fc00000);
+      if (EPI == EPI_SOFTMAX_XYZ && i < p.Ns) {
+        if (p.part) {
+          float* q = p.part + (((size_t)b * p.Ns + i) * gridDim.z + blockIdx.z) * 8;
+          q[0] = qnan; q[1] = qnan; q[2] = qnan; q[3] = qnan; q[4] = qnan;
+        } else {
+          float* o = p.out + (size_t)b * 3 * p.Ns + i;
+          o[0] = qnan; o[p.Ns] = qnan; o[2 * (size_t)p.Ns] = qnan;
+        }
+      }
+      if (EPI == EPI_KEYS && i < p.Ns) {
+        float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt;
+        for (int j = 0; j < p.Nt; ++j) dst[j] = qnan;
+      }
+    }
     if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns && p.part) {
       // split target range: leave (running max in log2 units, sum, sum*xyz) for the merge kernel
       float* q = p.part + (((size_t)b * p.Ns + i) * gridDim.z + blockIdx.z) * 8;
@@ -903,5 +921,9 @@ extern "C" int l3d_soft_correspondence_status(void) {
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpyFromSymbol(&v, g_softcorr_error, sizeof(int));
   if (e != cudaSuccess) return (int)e;
+  if (v != 0) {                    // report once, then clear: the word is not sticky across calls
+    const int zero = 0;
+    cudaMemcpyToSymbol(g_softcorr_error, &zero, sizeof(int));
+  }
   return v;
 }

@@ -18,6 +18,9 @@ class ChamferDistanceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
         p, q = _C.require_cuda(xyz1, "xyz1"), _C.require_cuda(xyz2, "xyz2")
+        if p.dim() != 3 or q.dim() != 3 or p.size(2) != 3 or q.size(2) != 3 or p.size(0) != q.size(0):
+            raise ValueError("ChamferDistance expects xyz1 [B, n, 3] and xyz2 [B, m, 3], got %s and %s"
+                             % (tuple(p.shape), tuple(q.shape)))
         B, n, m = p.size(0), p.size(1), q.size(1)
         d_pq, d_qp = p.new_empty((B, n)), p.new_empty((B, m))
         arg_pq = torch.empty((B, n), dtype=torch.int32, device=p.device)

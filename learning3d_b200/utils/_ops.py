@@ -7,6 +7,15 @@ import torch
 from .. import _C
 
 
+def _no_grad(name, *tensors):
+    """These reference functions are differentiable torch expressions; the kernels behind the drop-ins are
+    forward-only, so a gradient request is an error instead of a silently dropped gradient."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError("learning3d_b200.%s is forward-only: an input requires grad. Detach it (the models in "
+                           "learning3d only use this op to build indices / weights) or call it under "
+                           "torch.no_grad()." % name)
+
+
 def _xyz(t, name):
     t = _C.require_cuda(t, name)
     if t.dim() != 3 or t.size(2) != 3:
@@ -17,6 +26,7 @@ def _xyz(t, name):
 
 def square_distance(src, dst):
     """model_common_utils.py:19-38 — [B,N,3], [B,M,3] -> [B,N,M] expansion-form squared distance."""
+    _no_grad("square_distance", src, dst)
     src, dst = _xyz(src, "src"), _xyz(dst, "dst")
     B, N, _ = src.shape
     M = dst.shape[1]
@@ -117,6 +127,7 @@ def group_around(xyz, centres, idx, feats=None):
 
 def compute_density(xyz, bandwidth):
     """pointconv_util.py:199-209 — fused row reduction, the N x N matrix is never materialised."""
+    _no_grad("compute_density", xyz)
     xyz = _xyz(xyz, "xyz")
     B, N, _ = xyz.shape
     out = torch.empty((B, N), dtype=torch.float32, device=xyz.device)

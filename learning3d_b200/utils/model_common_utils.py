@@ -6,6 +6,7 @@ Reference: utils/model_common_utils.py:3-155.
 import torch
 
 from .. import _C
+from . import _ops
 
 
 def knn(x, k, add_one_to_k=False):
@@ -113,6 +114,7 @@ def get_graph_feature(x, k=20, device=None):
 def knn_point(k, pos1, pos2):
     """utils/model_common_utils.py:84-100.  pos1 [B,N,C] data, pos2 [B,M,C] queries ->
     (sqrt(d2) [B,M,k], idx [B,M,k] int64), nearest first."""
+    _ops._no_grad("knn_point", pos1, pos2)      # the reference's sqrt(d2) values are differentiable; ours are not
     pos1 = _C.require_cuda(pos1, "pos1")
     pos2 = _C.require_cuda(pos2, "pos2")
     B, N, C = pos1.shape
@@ -130,7 +132,6 @@ def knn_point(k, pos1, pos2):
 
 
 # ---- the remaining helpers of utils/model_common_utils.py --------------------------------------
-from . import _ops  # noqa: E402
 import numpy as np  # noqa: E402
 
 

@@ -14,6 +14,8 @@ Built here:
     ref_shims/emd_shim.cu.
 The extensions' OWN build files do not work any more (emd_torch: AT_CHECK / tensor.type() removed from
 torch 2.11; utils/lib: THC removed): only their kernels/launchers are compiled, in place.
+  * learning3d/ — the reference's Python package (+ three checkpoints) staged so that the GPU box can run
+    the reference's OWN models beside the rebound ones (stage_python below).
 """
 import os
 import sys
@@ -104,18 +106,51 @@ def build_emd():
     print("built", dst)
 
 
+def stage_python():
+    """Stage the reference's own Python package + the three checkpoints the C3/C4/C5 parity tests load under
+    oracle/_ref/learning3d/ (git-ignored like the .so files above, so it never enters the history, but it
+    travels to the GPU box with the snapshot).  The GPU tests import it as `learning3d`, run the UNMODIFIED
+    reference models on the B200 and compare them with the same models rebound to libl3d_b200.so
+    (tests/test_gpu_reference_models.py).  Nothing under learning3d_b200/ reads it."""
+    import shutil
+    dst = os.path.join(OUT, "learning3d")
+    n = 0
+    for sub in ("models", "utils", "losses", "ops", "data_utils"):
+        for root, _dirs, files in os.walk(os.path.join(REF, sub)):
+            rel = os.path.relpath(root, REF)
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                os.makedirs(os.path.join(dst, rel), exist_ok=True)
+                d = os.path.join(dst, rel, f)
+                s = os.path.join(root, f)
+                if not os.path.exists(d) or os.path.getmtime(d) < os.path.getmtime(s):
+                    shutil.copyfile(s, d)
+                    n += 1
+    for ck in ("exp_dcp/models/best_model.t7", "exp_flownet/models/model.best.t7", "exp_pcn/models/best_model.t7"):
+        s = os.path.join(REF, "pretrained", ck)
+        d = os.path.join(dst, "pretrained", ck)
+        if os.path.exists(s) and not os.path.exists(d):
+            os.makedirs(os.path.dirname(d), exist_ok=True)
+            shutil.copyfile(s, d)
+            n += 1
+    print("staged reference python: %d file(s) updated under %s" % (n, dst))
+
+
 def main():
     if not os.path.isdir(REF):
         print("no /root/reference here: keeping prebuilt oracle/_ref (if any)")
         return 0
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["chamfer", "pointnet2", "emd"]
+    which = sys.argv[1:] or ["chamfer", "pointnet2", "emd", "python"]
     if "chamfer" in which:
         build_chamfer()
     if "pointnet2" in which:
         build_pointnet2()
     if "emd" in which:
         build_emd()
+    if "python" in which:
+        stage_python()
     return 0
 
 

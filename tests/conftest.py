@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are skipped (not failed) on a host without CUDA, so a bare `pytest tests` is green there."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def pytest_sessionstart(session):
     """The suites need the built artefacts (libl3d_b200.so, oracle/liboracle.so).  They are normally built by
     __graft_entry__.build(); if a fresh checkout runs pytest first, build here (nvcc cross-compiles on CPU)."""
