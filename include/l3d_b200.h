@@ -327,6 +327,38 @@ int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* 
                                          const float* tgt_xyz_dev, int B, int D, int Ns, int Nt,
                                          float* src_corr_dev, float* scores_dev, void* stream);
 
+/* Testing hook: nonzero makes l3d_emd_forward take the multi-launch path (21 kernels) instead of the persistent
+ * cooperative launch (all 20 sweeps in one kernel with per-item barriers).  Both give identical results. */
+void l3d_debug_emd_force_multilaunch(int on);
+
+/* ---- EdgeConv stack of DGCNN (models/dgcnn.py:32-48, eval mode) ---------------------
+ *
+ * l3d_edgeconv_layer1: conv1 (6 -> 64, 1x1, bias-free) + folded BatchNorm + ReLU computed straight from the kNN
+ * indices — the [B,6,N,k] tensor of get_graph_feature (model_common_utils.py:132-155) is never written:
+ *   h1[b,c,n*k+j] = relu(scale[c] * (w[c,0:3] . x[:, idx[b,n,j]] + w[c,3:6] . x[:, n]) + shift[c])
+ * x_dev [B,3,N], idx_dev [B,N,k] int64 (l3d_knn_expansion's output); w_host [C1,6], scale_host, shift_host [C1]
+ * are HOST arrays (2 KB, passed to the kernel by value); C1 must be 64 (L3D_ERR_UNSUPPORTED otherwise).
+ * h1_dev [B,C1,N*k] and/or pool_dev (max over the k neighbours, written at
+ * pool_dev[b*pool_bstride + (pool_coff+c)*N + n]) may be NULL.
+ *
+ * l3d_conv1x1_bn_relu_maxk: one 1x1 convolution layer as a tensor-core GEMM (tcgen05 3xTF32, fp32 accumulate
+ * in TMEM), fused with folded BatchNorm, optional ReLU and the max over every group of G consecutive positions:
+ *   y[b,m,p]    = act(scale[m] * sum_k wt[k,m] * x[b,k,p] + shift[m])            -> h_out_dev [B,M,P]   (optional)
+ *   pool[b,m,n] = max_{j<G} y[b,m,n*G+j]   -> pool_out_dev[b*pool_bstride + (pool_coff+m)*(P/G) + n]   (optional)
+ * wt_dev [K,M] is the TRANSPOSED weight (conv.weight[M,K].t().contiguous()), x_dev [B,K,P].  EdgeConv layers
+ * 2-4 use G = k (P = N*k); conv5 uses G = 1, pool_out_dev = NULL.  Requires P % 4 == 0, M % 4 == 0, 16-byte
+ * aligned wt/x (L3D_ERR_UNSUPPORTED otherwise) and P % G == 0, G <= 256 when pooling.
+ * Accuracy: that of an fp32 GEMM (|err| <~ 2^-21 sum|w||x|).  No device synchronisation; a pipeline time-out
+ * (never observed) writes NaN to the outputs and is reported by l3d_edgeconv_status(). */
+int l3d_edgeconv_layer1(const float* x_dev, const int64_t* idx_dev, const float* w_host, const float* scale_host,
+                        const float* shift_host, int B, int N, int k, int C1, float* h1_dev, float* pool_dev,
+                        long long pool_bstride, int pool_coff, void* stream);
+int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const float* scale_dev,
+                             const float* shift_dev, int B, int M, int K, int P, int G, int relu, float* h_out_dev,
+                             float* pool_out_dev, long long pool_bstride, int pool_coff, void* stream);
+/* Synchronises the device; returns and clears the pipeline error word of l3d_conv1x1_bn_relu_maxk (0 = ok). */
+int l3d_edgeconv_status(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "l3d_emd_forward_ws_bytes": [_I, _I, _I],
     "l3d_emd_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "l3d_emd_backward_ws_bytes": [_I, _I, _I],
+    "l3d_debug_emd_force_multilaunch": [_I],
     "l3d_emd_backward": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "l3d_kabsch3x3_batched": [_P, _P, _P, _I, _P, _P, _P],
     "l3d_svd_head_tail": [_P, _P, _I, _I, _P, _P, _P],
@@ -61,6 +62,9 @@ _SIGNATURES = {
     "l3d_debug_soft_correspondence_split": [_I],
     "l3d_debug_soft_correspondence_tiles": [_P],
     "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_edgeconv_layer1": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
+    "l3d_conv1x1_bn_relu_maxk": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
+    "l3d_edgeconv_status": [],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "l3d_chamfer_ws_bytes": [_I, _I, _I],
@@ -71,6 +75,7 @@ _RESTYPE = {
     "l3d_error_string": ctypes.c_char_p,
     "l3d_launch_count": ctypes.c_uint64,
     "l3d_debug_force_slow_path": None,
+    "l3d_debug_emd_force_multilaunch": None,
     "l3d_debug_soft_correspondence_force_generic": None,
     "l3d_debug_soft_correspondence_split": None,
     "l3d_chamfer_ws_bytes": ctypes.c_size_t,

@@ -1,0 +1,563 @@
+// DGCNN's EdgeConv stack on the 5th-gen tensor cores (sm_100a: TMA + tcgen05 + TMEM), SURVEY.md §8f rank 1.
+//
+// Replaces models/dgcnn.py:32-48 in eval mode:
+//     x = get_graph_feature(xyz)                                [B, 6, N, k]   never written here
+//     x = relu(bn_i(conv_i(x)));  out_i = x.max(dim=-1)          i = 1..4       (64, 64, 128, 256 channels)
+//     y = relu(bn5(conv5(cat(out_1..out_4))))                                   [B, emb, N]
+//
+// Layer 1 (K = 6) is CUDA-core work straight from the kNN indices and the [B,3,N] cloud (edge_l1_kernel:
+// gather-on-load, the concatenated graph feature never exists).  Layers 2-4 and conv5 are GEMMs
+//     D[C_out, positions] = W[C_out, C_in] . X[C_in, positions]
+// with positions = (point, neighbour) pairs, run by ONE persistent kernel design (edge_gemm_kernel):
+//   * "swap-AB": the weights are the M-side operand (lane of the accumulator = output channel), the activations
+//     the N-side operand.  Both are MN-major fp32 in HBM exactly as torch holds them (W^T [C_in, C_out] prepared
+//     once per module, X = [B, C_in, N*k]), so 3-D tensor-map TMA drops [16 ch x 32] boxes into shared memory
+//     and the tensor core reads them in place (SWIZZLE_128B_ATOM_32B = UMMA layout 1) — no transposes.
+//   * fp32-class accuracy: 3xTF32 (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) like softcorr.cu: the raw fp32
+//     tile is the hi operand, four splitter warps derive the lo tiles shared-to-shared.
+//   * epilogue in the accumulator's own layout: thread = output channel, registers = consecutive positions, so
+//     folded BatchNorm + ReLU is one FFMA + FMNMX per value and the max over the k neighbours of a point is a
+//     running max over k consecutive registers — no shuffles, no atomics.  Tiles advance by a multiple of k
+//     positions (240 of the 256 MMA columns at k = 20) so that a group never straddles two tiles.
+//   * C_out = 256 / conv5: CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): each CTA keeps 128 output
+//     channels and stages only half of the activation columns.
+//   * persistent: one CTA (pair) per SM (TPC), static round-robin over (batch item, position tile, channel
+//     block) units; two 256-column accumulators in TMEM so the epilogue of unit i overlaps the MMAs of i+1.
+// Every mbarrier wait is bounded; a timed-out pipeline writes NaN to everything it still owed and raises the
+// error word read by l3d_edgeconv_status().
+#include "common.cuh"
+#include "tc05.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+#include <math.h>
+#include <mutex>
+#include <string.h>
+
+namespace l3d {
+
+constexpr int EC_EPI_THREADS = 128;
+constexpr int EC_SPLIT_THREADS = 128;
+constexpr int EC_THREADS = EC_EPI_THREADS + EC_SPLIT_THREADS + 64;   // + MMA warp + TMA warp
+constexpr int EC_BN = 256;           // positions per MMA (UMMA N)
+constexpr int EC_BK = 16;            // input channels per pipeline stage
+constexpr int EC_MAX_GROUPS = 16;    // pooled groups (points) per tile
+constexpr int EC_MAX_STAGES = 6;
+
+template <int CTAS>
+struct EdgeCfg {
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int BN_LOCAL = EC_BN / CTAS;            // activation columns staged by this CTA
+  static constexpr int A_TILE = SC_BM * EC_BK * 4;         // 8 KB   [16 ch x 128 out-channels]
+  static constexpr int B_TILE = BN_LOCAL * EC_BK * 4;      // 16 / 8 KB
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;    // W_hi, W_lo, X_hi, X_lo: 48 / 32 KB
+  static constexpr int ATOM = 32 * EC_BK * 4;              // one [16 ch x 32] TMA box
+  static constexpr int TMEM_COLS = 2 * EC_BN;
+};
+
+struct EdgeParams {
+  const float* scale;    // [M] folded BatchNorm scale  gamma / sqrt(var + eps)
+  const float* shift;    // [M] folded shift            beta - mean * scale
+  float* h_out;          // optional [B, M, P]: relu(bn(conv(x)))
+  float* pool_out;       // optional: max over each group of G positions -> pool_out[b*pool_bstride + (pool_coff+c)*pool_n + n]
+  long pool_bstride;
+  int pool_coff, pool_n;
+  int* err;
+  int B, M, K, P;        // batch, output channels, input channels, positions per item
+  int G, TS;             // positions per pooled group; tile stride in positions (multiple of G, <= 256)
+  int tiles_per_item, m_blocks, units;
+  int relu;
+};
+
+struct EdgeShared {
+  uint64_t tma_full[EC_MAX_STAGES];
+  uint64_t full[EC_MAX_STAGES];
+  uint64_t empty[EC_MAX_STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  alignas(16) float tbuf[EC_EPI_THREADS / 32][32][36];   // per-warp 32 x 32 transpose tile for the h_out stores
+  float pool[EC_EPI_THREADS][EC_MAX_GROUPS + 1];         // thread-private pooled values of the current tile
+};
+
+__device__ int g_edgeconv_error = 0;
+
+struct EdgeUnit { int b, j0, m0; };
+__device__ __forceinline__ EdgeUnit edge_unit(const EdgeParams& p, int u, int ctas, uint32_t crank) {
+  EdgeUnit r;
+  const int mb = u % p.m_blocks, q = u / p.m_blocks;
+  const int jt = q % p.tiles_per_item;
+  r.b = q / p.tiles_per_item;
+  r.j0 = jt * p.TS;
+  r.m0 = mb * (SC_BM * ctas) + (int)crank * SC_BM;
+  return r;
+}
+
+template <int CTAS>
+__global__ void __launch_bounds__(EC_THREADS, 1)
+edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_x) {
+  using Cfg = EdgeCfg<CTAS>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE, A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE;
+  constexpr bool PAIR = (CTAS == 2);
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  extern __shared__ unsigned char ec_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ec_raw) + 1023) & ~(uintptr_t)1023);
+  EdgeShared* sh = reinterpret_cast<EdgeShared*>(tiles + STAGES * STAGE_BYTES);
+  const uint32_t tiles_s = smem_u32(tiles);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cluster_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_clusters = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int my_tiles = (p.units > cluster_id) ? (p.units - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const int num_kb = (p.K + EC_BK - 1) / EC_BK;
+  const int total = my_tiles * num_kb;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sh->tma_full[s], 1);
+      mbar_init(&sh->full[s], EC_SPLIT_THREADS / 32 * CTAS);
+      mbar_init(&sh->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->acc_full[a], 1); mbar_init(&sh->acc_empty[a], EC_EPI_THREADS / 32 * CTAS); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "n"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "n"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------ epilogue: BN + ReLU, max over groups of G positions, stores
+    const float qnan = __int_as_float(0x7fc00000);
+    bool ok = true;
+    for (int t = 0; t < my_tiles; ++t) {
+      const EdgeUnit un = edge_unit(p, cluster_id + t * n_clusters, CTAS, crank);
+      const int a = t & 1;
+      const int c = un.m0 + tid;                    // this thread's output channel
+      const bool vrow = c < p.M;
+      const int nvalid = min(p.TS, p.P - un.j0);    // positions this tile owns
+      const bool vec = ((p.P & 3) == 0) && ((un.j0 & 3) == 0) && ((nvalid & 3) == 0);
+      if (ok && !mbar_wait_bounded(&sh->acc_full[a], (uint32_t)((t >> 1) & 1))) {
+        ok = false;
+        atomicCAS(p.err, 0, 1);
+      }
+      if (!ok) {
+        // the pipeline is dead: everything this thread still owed becomes NaN so that no caller mistakes
+        // uninitialised memory for a result
+        if (vrow) {
+          if (p.h_out) {
+            float* dst = p.h_out + ((size_t)un.b * p.M + c) * p.P + un.j0;
+            for (int e = 0; e < nvalid; ++e) dst[e] = qnan;
+          }
+          if (p.pool_out) {
+            float* dst = p.pool_out + (size_t)un.b * p.pool_bstride + (size_t)(p.pool_coff + c) * p.pool_n + un.j0 / p.G;
+            for (int g = 0; g < nvalid / p.G; ++g) dst[g] = qnan;
+          }
+        }
+        continue;
+      }
+      __syncwarp();
+      tc_fence_after();
+      const float s = vrow ? __ldg(p.scale + c) : 0.f, sf = vrow ? __ldg(p.shift + c) : 0.f;
+      float gm = -INFINITY;
+      int cnt = 0, gi = 0;
+#pragma unroll 1
+      for (int ch = 0; ch < EC_BN / 32; ++ch) {
+        if (ch * 32 >= nvalid) break;
+        float v[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * EC_BN + ch * 32), v);
+        const int nv = min(32, nvalid - ch * 32);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float y = fmaf(v[e], s, sf);
+          v[e] = p.relu ? fmaxf(y, 0.f) : y;
+        }
+        if (p.h_out) {
+          if (vec) {
+            // transpose the warp's 32 x 32 block through shared memory: every store instruction then writes
+            // four (partly) complete 128-byte lines instead of 16-byte pieces of 32 different rows
+            float(*tb)[36] = sh->tbuf[warp];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(&tb[lane][e]) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            __syncwarp();
+            const int rr = lane >> 3, cc = (lane & 7) * 4;
+            const int cbase = un.m0 + warp * 32;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(&tb[r + rr][cc]);
+              const int cr = cbase + r + rr;
+              if (cr < p.M && cc < nv)
+                *reinterpret_cast<float4*>(p.h_out + ((size_t)un.b * p.M + cr) * p.P + un.j0 + ch * 32 + cc) = o;
+            }
+            __syncwarp();
+          } else if (vrow) {
+            float* dst = p.h_out + ((size_t)un.b * p.M + c) * p.P + un.j0 + ch * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nv) dst[e] = v[e];
+          }
+        }
+        if (p.pool_out) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < nv) {
+              gm = fmaxf(gm, v[e]);
+              if (++cnt == p.G) { sh->pool[tid][gi++] = gm; gm = -INFINITY; cnt = 0; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);
+        else mbar_arrive(&sh->acc_empty[a]);
+      }
+      if (p.pool_out && vrow) {
+        float* dst = p.pool_out + (size_t)un.b * p.pool_bstride + (size_t)(p.pool_coff + c) * p.pool_n + un.j0 / p.G;
+        for (int g = 0; g < gi; ++g) dst[g] = sh->pool[tid][g];
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------ splitters: lo = tf32(x - trunc_tf32(x)), smem -> smem
+    const int r = tid - EC_EPI_THREADS;
+    bool ok = true;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % STAGES;
+      const uint32_t n = (uint32_t)(it / STAGES);
+      const uint32_t st = tiles_s + s * STAGE_BYTES;
+      if (!mbar_wait_bounded(&sh->tma_full[s], n & 1u)) { ok = false; break; }
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        const uint32_t hi = st + (op ? 2 * A_TILE : 0), lo = hi + (op ? B_TILE : A_TILE);
+#pragma unroll
+        for (int q = 0; q < (op ? B_TILE : A_TILE) / 16 / EC_SPLIT_THREADS; ++q) {
+          const uint32_t off = (uint32_t)(q * EC_SPLIT_THREADS + r) * 16u;
+          const uint4 x = lds128(hi + off);
+          uint4 y;
+          y.x = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(x.x & 0xffffe000u))));
+          y.y = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(x.y & 0xffffe000u))));
+          y.z = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(x.z & 0xffffe000u))));
+          y.w = rna_tf32_bits(__float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(x.w & 0xffffe000u))));
+          sts128(lo + off, y);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&sh->full[s], 0);
+        else mbar_arrive(&sh->full[s]);
+      }
+    }
+    if (!ok) atomicCAS(p.err, 0, 2);
+  } else if (warp == 8) {
+    // ------------------------------------------------ MMA issuer (rank 0 of a pair issues for both CTAs)
+    bool ok = true;
+    int it = 0;
+    for (int t = 0; t < my_tiles && ok && crank == 0; ++t) {
+      const int a = t & 1;
+      const uint32_t pe = (uint32_t)(((t >> 1) & 1) ^ 1);
+      if (!(PAIR ? mbar_wait_bounded_cluster(&sh->acc_empty[a], pe) : mbar_wait_bounded(&sh->acc_empty[a], pe))) { ok = false; break; }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + (uint32_t)(a * EC_BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t n = (uint32_t)(it / STAGES);
+        if (!(PAIR ? mbar_wait_bounded_cluster(&sh->full[s], n & 1u) : mbar_wait_bounded(&sh->full[s], n & 1u))) { ok = false; break; }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tiles_s + s * STAGE_BYTES;
+          // MN-major tf32 operands: UMMA layout 1 (128 B swizzle, 32-byte atoms): 4-channel groups 512 B apart,
+          // the next 32 rows / columns one TMA box (ATOM bytes) further
+          constexpr uint32_t lbo = (uint32_t)Cfg::ATOM, sbo = 512u, lay = 1u;
+          constexpr uint32_t idesc = sc_idesc(EC_BN, true, SC_BM * CTAS);
+          const uint64_t a_hi = sc_desc(sa, lbo, sbo, lay), a_lo = sc_desc(sa + A_TILE, lbo, sbo, lay);
+          const uint64_t b_hi = sc_desc(sa + 2 * A_TILE, lbo, sbo, lay), b_lo = sc_desc(sa + 2 * A_TILE + B_TILE, lbo, sbo, lay);
+#pragma unroll
+          for (int k = 0; k < EC_BK / SC_UK; ++k) {
+            const uint64_t adv = (uint64_t)((k * 1024) >> 4);     // next 8-channel group
+            if (PAIR) {
+              tc_mma_tf32_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              tc_mma_tf32_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          if (PAIR) {
+            tc_commit_pair(&sh->empty[s]);
+            if (kb == num_kb - 1) tc_commit_pair(&sh->acc_full[a]);
+          } else {
+            tc_commit(&sh->empty[s]);
+            if (kb == num_kb - 1) tc_commit(&sh->acc_full[a]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (!ok && lane == 0) atomicCAS(p.err, 0, 3);
+  } else {
+    // ------------------------------------------------ TMA issuer: 4 weight boxes + 8 (4 in a pair) activation boxes
+    bool ok = true;
+    int it = 0;
+    for (int t = 0; t < my_tiles && ok; ++t) {
+      const EdgeUnit un = edge_unit(p, cluster_id + t * n_clusters, CTAS, crank);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t n = (uint32_t)(it / STAGES);
+        if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }
+        if (lane == 0) {
+          const uint32_t st = tiles_s + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&sh->tma_full[s], A_TILE + B_TILE);
+#pragma unroll
+          for (int q = 0; q < SC_BM / 32; ++q)
+            tma_load_3d(st + q * Cfg::ATOM, &tmap_w, un.m0 + 32 * q, kb * EC_BK, 0, &sh->tma_full[s]);
+#pragma unroll
+          for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
+            tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_x, un.j0 + (int)crank * Cfg::BN_LOCAL + 32 * q, kb * EC_BK,
+                        un.b, &sh->tma_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    if (!ok && lane == 0) atomicCAS(p.err, 0, 4);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+template <int CTAS>
+static size_t edge_smem_bytes() {
+  return (size_t)EdgeCfg<CTAS>::STAGES * EdgeCfg<CTAS>::STAGE + sizeof(EdgeShared) + 1024;
+}
+
+// ---- layer 1: conv(6 -> C1) + BN + ReLU straight from the kNN indices (gather-on-load) ------------------------
+// h1[b, c, n*k + j] = relu(scale_c * (W[c,0:3] . x[idx[b,n,j]] + W[c,3:6] . x[n]) + shift_c)
+// (get_graph_feature's channel order: neighbour xyz, then centre xyz — model_common_utils.py:149-154).
+// Weights travel as a kernel parameter (constant bank): every FFMA reads its weight as an immediate-like operand.
+constexpr int EC_C1 = 64;
+struct EdgeL1Weights {
+  float w[EC_C1 * 6];
+  float scale[EC_C1];
+  float shift[EC_C1];
+};
+
+__device__ __forceinline__ float edge_l1_value(const EdgeL1Weights& W, int c, float nx, float ny, float nz, float cx,
+                                               float cy, float cz) {
+  float v = __fmul_rn(W.w[c * 6 + 0], nx);
+  v = fmaf(W.w[c * 6 + 1], ny, v);
+  v = fmaf(W.w[c * 6 + 2], nz, v);
+  v = fmaf(W.w[c * 6 + 3], cx, v);
+  v = fmaf(W.w[c * 6 + 4], cy, v);
+  v = fmaf(W.w[c * 6 + 5], cz, v);
+  return fmaxf(fmaf(v, W.scale[c], W.shift[c]), 0.f);
+}
+
+// thread = position (n, j): 64 coalesced stores
+__global__ void __launch_bounds__(256) edge_l1_kernel(const __grid_constant__ EdgeL1Weights W, const float* __restrict__ x,
+                                                      const long long* __restrict__ idx, int N, int k,
+                                                      float* __restrict__ h1) {
+  const int b = blockIdx.y;
+  const long P = (long)N * k;
+  const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= P) return;
+  const int n = (int)(pos / k);
+  const float* xb = x + (size_t)b * 3 * N;
+  long j = idx[(size_t)b * P + pos];
+  if ((unsigned long)j >= (unsigned long)N) j = n;            // never produced by l3d_knn_*; keeps the loads in bounds
+  const float nx = __ldg(xb + j), ny = __ldg(xb + N + j), nz = __ldg(xb + 2 * (size_t)N + j);
+  const float cx = __ldg(xb + n), cy = __ldg(xb + N + n), cz = __ldg(xb + 2 * (size_t)N + n);
+  float* o = h1 + (size_t)b * EC_C1 * P + pos;
+#pragma unroll
+  for (int c = 0; c < EC_C1; ++c) o[(size_t)c * P] = edge_l1_value(W, c, nx, ny, nz, cx, cy, cz);
+}
+
+// thread = point n: max over its k neighbours of the same expression (bit-identical values), coalesced over n
+__global__ void __launch_bounds__(128) edge_l1_pool_kernel(const __grid_constant__ EdgeL1Weights W,
+                                                           const float* __restrict__ x, const long long* __restrict__ idx,
+                                                           int N, int k, float* __restrict__ pool, long pool_bstride,
+                                                           int pool_coff) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* xb = x + (size_t)b * 3 * N;
+  const float cx = __ldg(xb + n), cy = __ldg(xb + N + n), cz = __ldg(xb + 2 * (size_t)N + n);
+  float m[EC_C1];
+#pragma unroll
+  for (int c = 0; c < EC_C1; ++c) m[c] = 0.f;                    // values are >= 0 after the ReLU
+  const long long* ip = idx + ((size_t)b * N + n) * k;
+  for (int jj = 0; jj < k; ++jj) {
+    long j = ip[jj];
+    if ((unsigned long)j >= (unsigned long)N) j = n;
+    const float nx = __ldg(xb + j), ny = __ldg(xb + N + j), nz = __ldg(xb + 2 * (size_t)N + j);
+#pragma unroll
+    for (int c = 0; c < EC_C1; ++c) m[c] = fmaxf(m[c], edge_l1_value(W, c, nx, ny, nz, cx, cy, cz));
+  }
+  float* o = pool + (size_t)b * pool_bstride + (size_t)pool_coff * N + n;
+#pragma unroll
+  for (int c = 0; c < EC_C1; ++c) o[(size_t)c * N] = m[c];
+}
+
+}  // namespace l3d
+
+using namespace l3d;
+
+static int edge_sm_count(int dev) {
+  static thread_local int c_dev = -1, c_n = 148;
+  if (c_dev != dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c_n = n;
+    c_dev = dev;
+  }
+  return c_n;
+}
+
+extern "C" int l3d_edgeconv_layer1(const float* x_dev, const int64_t* idx_dev, const float* w_host,
+                                   const float* scale_host, const float* shift_host, int B, int N, int k, int C1,
+                                   float* h1_dev, float* pool_dev, long long pool_bstride, int pool_coff,
+                                   void* stream) {
+  if (B < 0 || N < 1 || k < 1 || k > N) return L3D_ERR_INVALID;
+  if (C1 != EC_C1) return L3D_ERR_UNSUPPORTED;
+  if (B == 0) return L3D_OK;
+  if (!x_dev || !idx_dev || !w_host || !scale_host || !shift_host || (!h1_dev && !pool_dev) || B > 65535)
+    return L3D_ERR_INVALID;
+  EdgeL1Weights W;
+  memcpy(W.w, w_host, sizeof(W.w));
+  memcpy(W.scale, scale_host, sizeof(W.scale));
+  memcpy(W.shift, shift_host, sizeof(W.shift));
+  const long P = (long)N * k;
+  if (h1_dev) {
+    edge_l1_kernel<<<dim3((unsigned)((P + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
+        W, x_dev, reinterpret_cast<const long long*>(idx_dev), N, k, h1_dev);
+    count_launch();
+    L3D_LAUNCH_CHECK();
+  }
+  if (pool_dev) {
+    edge_l1_pool_kernel<<<dim3((unsigned)((N + 127) / 128), B), 128, 0, (cudaStream_t)stream>>>(
+        W, x_dev, reinterpret_cast<const long long*>(idx_dev), N, k, pool_dev, (long)pool_bstride, pool_coff);
+    count_launch();
+    L3D_LAUNCH_CHECK();
+  }
+  return L3D_OK;
+}
+
+// relu(scale * (W . X) + shift) for X [B, K, P], W^T [K, M]; optional full output h_out [B, M, P] and optional max
+// over every group of G consecutive positions -> pool_out[b*pool_bstride + (pool_coff + c)*(P/G) + n].
+extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const float* scale_dev,
+                                        const float* shift_dev, int B, int M, int K, int P, int G, int relu,
+                                        float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
+                                        void* stream) {
+  if (B < 0 || M < 1 || K < 1 || P < 1 || G < 1) return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  if (!wt_dev || !x_dev || !scale_dev || !shift_dev || (!h_out_dev && !pool_out_dev)) return L3D_ERR_INVALID;
+  if (pool_out_dev && (P % G != 0 || G > EC_BN)) return L3D_ERR_INVALID;
+  // TMA: 16-byte global strides and bases
+  if ((P & 3) || (M & 3) || ((((uintptr_t)wt_dev) | ((uintptr_t)x_dev)) & 15)) return L3D_ERR_UNSUPPORTED;
+  if (B > 65535) return L3D_ERR_UNSUPPORTED;
+  EdgeParams p;
+  memset(&p, 0, sizeof(p));
+  p.scale = scale_dev; p.shift = shift_dev; p.h_out = h_out_dev; p.pool_out = pool_out_dev;
+  p.pool_bstride = (long)pool_bstride; p.pool_coff = pool_coff;
+  p.B = B; p.M = M; p.K = K; p.P = P; p.G = G; p.relu = relu;
+  if (pool_out_dev) {
+    int groups = EC_BN / G;
+    if (groups > EC_MAX_GROUPS) groups = EC_MAX_GROUPS;
+    p.TS = groups * G;
+    p.pool_n = P / G;
+  } else {
+    p.TS = EC_BN;
+    p.pool_n = 0;
+  }
+  const bool pair = M > SC_BM;
+  p.tiles_per_item = (P + p.TS - 1) / p.TS;
+  p.m_blocks = (M + (pair ? 2 : 1) * SC_BM - 1) / ((pair ? 2 : 1) * SC_BM);
+  const long units = (long)B * p.tiles_per_item * p.m_blocks;
+  if (units > 0x7fffffffL) return L3D_ERR_UNSUPPORTED;
+  p.units = (int)units;
+
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    static std::mutex mu;
+    static uint64_t done_mask = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 64 || !(done_mask >> dev & 1)) {
+      cudaError_t e = cudaFuncSetAttribute(edge_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(edge_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
+      if (e != cudaSuccess) return (int)e;
+      if (dev < 64) done_mask |= (uint64_t)1 << dev;
+    }
+  }
+  void* errp = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&errp, g_edgeconv_error);
+  if (e != cudaSuccess) return (int)e;
+  p.err = (int*)errp;
+
+  CUtensorMap mw, mx;
+  memset(&mw, 0, sizeof(mw)); memset(&mx, 0, sizeof(mx));
+  if (!make_dn_tmap(&mw, wt_dev, 1, K, M, EC_BK) || !make_dn_tmap(&mx, x_dev, B, K, P, EC_BK)) return L3D_ERR_UNSUPPORTED;
+
+  const int sms = edge_sm_count(dev);
+  if (pair) {
+    long clusters = sms / 2;
+    if (clusters > units) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(EC_THREADS);
+    cfg.dynamicSmemBytes = edge_smem_bytes<2>();
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2>, p, mw, mx);
+    if (le != cudaSuccess) return (int)le;
+  } else {
+    long grid = sms;
+    if (grid > units) grid = units;
+    edge_gemm_kernel<1><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
+  }
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+// Synchronises the device and returns (then clears) the pipeline error word of l3d_conv1x1_bn_relu_maxk:
+// 0 = ok; 1/2/3/4 = an epilogue / splitter / MMA-issuer / TMA-issuer wait ran out (outputs were set to NaN).
+extern "C" int l3d_edgeconv_status(void) {
+  int v = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyFromSymbol(&v, g_edgeconv_error, sizeof(int));
+  if (e != cudaSuccess) return (int)e;
+  if (v != 0) {
+    const int zero = 0;
+    cudaMemcpyToSymbol(g_edgeconv_error, &zero, sizeof(int));
+  }
+  return v;
+}

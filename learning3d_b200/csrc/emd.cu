@@ -23,6 +23,8 @@
 #include "../../include/l3d_b200.h"
 #include "launch_count.h"
 
+#include <algorithm>
+
 namespace l3d {
 
 constexpr int EMD_THREADS = 256;
@@ -79,76 +81,174 @@ struct EmdSweepParams {
   int init;                // ph1 of the first level: remain = multi
 };
 
+// One weighted row sweep for the rows [row_begin, row_end) of batch item b, executed by one CTA (8 warps x 4 rows
+// per pass).  COHERENT: the column weights / row state were written by OTHER CTAs of the same launch (persistent
+// kernel, after a per-item barrier), so they are read with ld.global.cg (L2) instead of through L1.
+template <bool FUSED, bool COHERENT>
+__device__ __forceinline__ void emd_sweep_rows(const EmdSweepParams& p, int b, int row_begin, int row_end,
+                                               float4* s_col, float* s_vb) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* rows = p.rows + (size_t)b * p.nr * 3;
+  const float* cols = p.cols + (size_t)b * p.nc * 3;
+  auto ldv = [](const float* q) -> float { return COHERENT ? __ldcg(q) : *q; };
+  for (int base = row_begin; base < row_end; base += EMD_ROWS_PER_CTA) {
+    const int r0 = base + warp * EMD_R;
+    float rx[EMD_R], ry[EMD_R], rz[EMD_R], sa[EMD_R], sb[EMD_R];
+#pragma unroll
+    for (int i = 0; i < EMD_R; ++i) {
+      const int r = min(r0 + i, p.nr - 1);
+      rx[i] = rows[r * 3]; ry[i] = rows[r * 3 + 1]; rz[i] = rows[r * 3 + 2];
+      sa[i] = 0.f; sb[i] = 0.f;
+    }
+    for (int c0 = 0; c0 < p.nc; c0 += EMD_CHUNK) {
+      const int cn = min(EMD_CHUNK, p.nc - c0);
+      __syncthreads();
+      for (int c = tid; c < cn; c += EMD_THREADS) {
+        const float* q = cols + (size_t)(c0 + c) * 3;
+        s_col[c] = make_float4(q[0], q[1], q[2], ldv(p.vA + (size_t)b * p.nc + c0 + c));
+        if (FUSED) s_vb[c] = ldv(p.vB + (size_t)b * p.nc + c0 + c);
+      }
+      __syncthreads();
+      if (r0 < row_end) {
+        for (int c = lane; c < cn; c += 32) {
+          const float4 q = s_col[c];
+          const float vb = FUSED ? s_vb[c] : 0.f;
+#pragma unroll
+          for (int i = 0; i < EMD_R; ++i) {
+            const float d2 = emd_d2(rx[i], ry[i], rz[i], q.x, q.y, q.z);
+            sa[i] = fmaf(emd_exp(p.lvlA, d2), q.w, sa[i]);
+            if (FUSED) sb[i] = fmaf(emd_exp(p.lvlB, d2), vb, sb[i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < EMD_R; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sa[i] += __shfl_xor_sync(L3D_FULL_MASK, sa[i], o);
+        if (FUSED) sb[i] += __shfl_xor_sync(L3D_FULL_MASK, sb[i], o);
+      }
+    }
+    if (lane < EMD_R) {
+      float S = sa[0], S2 = sb[0];
+#pragma unroll
+      for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = sa[i]; S2 = sb[i]; }
+      const int r = r0 + lane;
+      if (r < row_end && r < p.nr) {
+        const size_t o = (size_t)b * p.nr + r;
+        if (p.phase == EMD_PH1) {
+          const float rem = p.init ? p.multi : ldv(p.remain + o);
+          if (p.init) p.remain[o] = rem;
+          p.ratio_out[o] = rem / (1e-9f + S);                       // emd.cuh:40,60
+        } else if (p.phase == EMD_PH2) {
+          const float rem = p.init ? p.multi : ldv(p.remain + o);   // init: remainR = multiR (emd.cuh:24-25)
+          const float sumr = S * rem;                                 // emd.cuh:110
+          const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+          p.ratio_out[o] = consumption * rem;
+          p.remain[o] = fmaxf(0.0f, rem - sumr);
+        } else {
+          // finish level j: remainL = max(0, remainL - ratioL_j * S_j)   (emd.cuh:157-168) ...
+          const float rem = fmaxf(0.0f, ldv(p.remain + o) - ldv(p.ratio_in + o) * S);
+          p.remain[o] = rem;
+          // ... and start level j+1: ratioL_{j+1} = remainL / (1e-9 + S_{j+1})
+          p.ratio_out[o] = rem / (1e-9f + S2);
+        }
+      }
+    }
+  }
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(const EmdSweepParams p) {
   __shared__ float4 s_col[EMD_CHUNK];
   __shared__ float s_vb[FUSED ? EMD_CHUNK : 1];
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = blockIdx.x * EMD_ROWS_PER_CTA + warp * EMD_R;
-  const float* rows = p.rows + (size_t)b * p.nr * 3;
-  const float* cols = p.cols + (size_t)b * p.nc * 3;
+  const int r0 = blockIdx.x * EMD_ROWS_PER_CTA;
+  emd_sweep_rows<FUSED, false>(p, blockIdx.y, r0, min(r0 + EMD_ROWS_PER_CTA, p.nr), s_col, s_vb);
+}
 
-  float rx[EMD_R], ry[EMD_R], rz[EMD_R], sa[EMD_R], sb[EMD_R];
-#pragma unroll
-  for (int i = 0; i < EMD_R; ++i) {
-    const int r = min(r0 + i, p.nr - 1);
-    rx[i] = rows[r * 3]; ry[i] = rows[r * 3 + 1]; rz[i] = rows[r * 3 + 2];
-    sa[i] = 0.f; sb[i] = 0.f;
+// ---- persistent forward: all 20 sweeps in ONE launch --------------------------------------------------------
+// The sweeps of one batch item depend on each other only through the per-item vectors (remainL/R, ratioL/R), so
+// the CTAs of an item synchronise among THEMSELVES (a monotonically increasing arrival counter per item in global
+// memory, release/acquire at gpu scope) — no grid-wide barrier, items drift apart freely.  Every CTA of the grid
+// must be co-resident (the host sizes the grid from the occupancy query).  Replaces the 20 sweep launches + the
+// fill launch of the multi-launch path (kept below for batches too large to be co-resident).
+struct EmdPersistParams {
+  const float* xyz1; const float* xyz2;
+  float* remainL; float* remainR;      // [B,n], [B,m]
+  float* ratioL; float* ratioR;        // [LEVELS,B,n], [LEVELS,B,m]
+  unsigned int* arrive;                // [B] zero-initialised arrival counters
+  unsigned int* err;                   // zero-initialised error word (barrier time-out)
+  int B, n, m, ctas_per_item;
+  float multiL, multiR;
+  float lvl[EMD_LEVELS];
+};
+
+// false = the other CTAs of the item never arrived (cannot happen under a cooperative launch; bounded so that
+// a bug is an error word and NaN costs, never a hung GPU)
+__device__ __forceinline__ bool emd_item_barrier(unsigned int* ctr, unsigned int target, unsigned int* err,
+                                                 int* s_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v = 0;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target && ++spins < (1ull << 26) && *(volatile unsigned int*)err == 0u);
+    if (v < target) atomicExch(err, 1u);
+    *s_flag = (v >= target) ? 1 : 0;
+    __threadfence();
   }
-  for (int c0 = 0; c0 < p.nc; c0 += EMD_CHUNK) {
-    const int cn = min(EMD_CHUNK, p.nc - c0);
-    __syncthreads();
-    for (int c = tid; c < cn; c += EMD_THREADS) {
-      const float* q = cols + (size_t)(c0 + c) * 3;
-      s_col[c] = make_float4(q[0], q[1], q[2], p.vA[(size_t)b * p.nc + c0 + c]);
-      if (FUSED) s_vb[c] = p.vB[(size_t)b * p.nc + c0 + c];
-    }
-    __syncthreads();
-    for (int c = lane; c < cn; c += 32) {
-      const float4 q = s_col[c];
-      const float vb = FUSED ? s_vb[c] : 0.f;
-#pragma unroll
-      for (int i = 0; i < EMD_R; ++i) {
-        const float d2 = emd_d2(rx[i], ry[i], rz[i], q.x, q.y, q.z);
-        sa[i] = fmaf(emd_exp(p.lvlA, d2), q.w, sa[i]);
-        if (FUSED) sb[i] = fmaf(emd_exp(p.lvlB, d2), vb, sb[i]);
-      }
-    }
+  __syncthreads();
+  return *s_flag != 0;
+}
+
+__global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPersistParams q) {
+  __shared__ float4 s_col[EMD_CHUNK];
+  __shared__ float s_vb[EMD_CHUNK];
+  __shared__ int s_flag;
+  const int C = q.ctas_per_item;
+  const int b = blockIdx.x / C, cx = blockIdx.x - b * C;
+  // contiguous row shares in both clouds, rounded up to whole warps' worth of rows
+  auto share = [&](int nr, int& r0, int& r1) {
+    const int per = ((nr + C - 1) / C + EMD_R - 1) / EMD_R * EMD_R;
+    r0 = min(nr, cx * per); r1 = min(nr, r0 + per);
+  };
+  int l0, l1, r0, r1;
+  share(q.n, l0, l1);
+  share(q.m, r0, r1);
+  unsigned int* ctr = q.arrive + b;
+  unsigned int phase = 0;
+  const size_t Bn = (size_t)q.B * q.n, Bm = (size_t)q.B * q.m;
+  // remainR = multiR before anybody sweeps over it
+  for (int r = r0 + (int)threadIdx.x; r < r1; r += EMD_THREADS) q.remainR[(size_t)b * q.m + r] = q.multiR;
+  if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
+  {
+    EmdSweepParams p{};
+    p.rows = q.xyz1; p.cols = q.xyz2; p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH1;
+    p.lvlA = q.lvl[0]; p.vA = q.remainR; p.remain = q.remainL; p.ratio_out = q.ratioL; p.multi = q.multiL; p.init = 1;
+    emd_sweep_rows<false, true>(p, b, l0, l1, s_col, s_vb);
   }
-#pragma unroll
-  for (int i = 0; i < EMD_R; ++i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sa[i] += __shfl_xor_sync(L3D_FULL_MASK, sa[i], o);
-      if (FUSED) sb[i] += __shfl_xor_sync(L3D_FULL_MASK, sb[i], o);
+  if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
+  for (int it = 0; it < EMD_LEVELS; ++it) {
+    {
+      EmdSweepParams p{};
+      p.rows = q.xyz2; p.cols = q.xyz1; p.B = q.B; p.nr = q.m; p.nc = q.n; p.phase = EMD_PH2;
+      p.lvlA = q.lvl[it]; p.vA = q.ratioL + (size_t)it * Bn; p.remain = q.remainR; p.ratio_out = q.ratioR + (size_t)it * Bm;
+      emd_sweep_rows<false, true>(p, b, r0, r1, s_col, s_vb);
     }
-  }
-  if (lane < EMD_R) {
-    float S = sa[0], S2 = sb[0];
-#pragma unroll
-    for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = sa[i]; S2 = sb[i]; }
-    const int r = r0 + lane;
-    if (r < p.nr) {
-      const size_t o = (size_t)b * p.nr + r;
-      if (p.phase == EMD_PH1) {
-        const float rem = p.init ? p.multi : p.remain[o];
-        if (p.init) p.remain[o] = rem;
-        p.ratio_out[o] = rem / (1e-9f + S);                       // emd.cuh:40,60
-      } else if (p.phase == EMD_PH2) {
-        const float rem = p.remain[o];
-        const float sumr = S * rem;                                 // emd.cuh:110
-        const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
-        p.ratio_out[o] = consumption * rem;
-        p.remain[o] = fmaxf(0.0f, rem - sumr);
-      } else {
-        // finish level j: remainL = max(0, remainL - ratioL_j * S_j)   (emd.cuh:157-168) ...
-        const float rem = fmaxf(0.0f, p.remain[o] - p.ratio_in[o] * S);
-        p.remain[o] = rem;
-        // ... and start level j+1: ratioL_{j+1} = remainL / (1e-9 + S_{j+1})
-        p.ratio_out[o] = rem / (1e-9f + S2);
-      }
+    if (it + 1 == EMD_LEVELS) break;
+    if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
+    {
+      EmdSweepParams p{};
+      p.rows = q.xyz1; p.cols = q.xyz2; p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH3_PH1;
+      p.lvlA = q.lvl[it]; p.vA = q.ratioR + (size_t)it * Bm; p.lvlB = q.lvl[it + 1]; p.vB = q.remainR;
+      p.remain = q.remainL; p.ratio_in = q.ratioL + (size_t)it * Bn; p.ratio_out = q.ratioL + (size_t)(it + 1) * Bn;
+      emd_sweep_rows<true, true>(p, b, l0, l1, s_col, s_vb);
     }
+    if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
   }
 }
 
@@ -163,6 +263,7 @@ struct EmdFinalParams {
   float* partial;                         // [B, gridDim.x]
   float* cost;                            // [B]
   unsigned int* ticket;                   // [B] self-resetting
+  const unsigned int* err;                // optional: nonzero = the persistent sweeps timed out -> cost = NaN
   int B, n, m;
   float lvl[EMD_LEVELS];
 };
@@ -217,7 +318,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_final_kernel(const EmdFinalPa
     if (tid == 0) {
       float s = 0.f;
       for (int w = 0; w < EMD_WARPS; ++w) s += red[w];
-      p.cost[b] = s;
+      p.cost[b] = (p.err && *p.err) ? __int_as_float(0x7fc00000) : s;
       p.ticket[b] = 0u;
     }
   }
@@ -306,11 +407,15 @@ static int emd_slices(int B, int n, int m) {
 
 using namespace l3d;
 
+static int g_emd_force_multilaunch = 0;
+// Testing hook: nonzero forces the multi-launch (21 kernels) forward path instead of the persistent one.
+extern "C" void l3d_debug_emd_force_multilaunch(int on) { g_emd_force_multilaunch = on ? 1 : 0; }
+
 // workspace layout (floats): remainL[B,n] remainR[B,m] ratioL[LEVELS,B,n] ratioR[LEVELS,B,m]
-//                            partial[B*gx] | ticket[B] (uint)
+//                            partial[B*gx] | ticket[B] arrive[B] err[1] (uint)
 static size_t emd_fwd_ws_floats(int B, int n, int m) {
   const size_t gx = (size_t)(m + EMD_WARPS - 1) / EMD_WARPS;
-  return (size_t)B * n + (size_t)B * m + (size_t)B * EMD_LEVELS * ((size_t)n + m) + (size_t)B * gx + (size_t)B;
+  return (size_t)B * n + (size_t)B * m + (size_t)B * EMD_LEVELS * ((size_t)n + m) + (size_t)B * gx + 2 * (size_t)B + 1;
 }
 extern "C" size_t l3d_emd_forward_ws_bytes(int B, int n, int m) {
   if (B < 1 || n < 1 || m < 1) return 0;
@@ -339,6 +444,52 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
   // multiL / multiR with the reference's INTEGER division (emd.cuh:10-16)
   const float multiL = (n >= m) ? 1.f : (float)(m / n);
   const float multiR = (n >= m) ? (float)(n / m) : 1.f;
+  unsigned int* arrive = ticket + B;
+  unsigned int* errw = arrive + B;
+  EmdFinalParams fp{};
+  for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it);
+
+  // ---- persistent path: one cooperative launch runs all 20 sweeps (per-item barriers) ---------------------
+  bool persistent = g_emd_force_multilaunch == 0;
+  int ctas_per_item = 0;
+  if (persistent) {
+    static thread_local int c_dev = -1, c_cap = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != c_dev) {
+      int occ = 0, sms = 0, coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, emd_persistent_kernel, EMD_THREADS, 0) != cudaSuccess) occ = 0;
+      if (occ > 2) occ = 2;                 // 16 warps/SM already cover the MUFU latency; fewer CTAs = cheaper barriers
+      c_cap = coop ? sms * occ : 0;
+      c_dev = dev;
+    }
+    const int want = (std::max(n, m) + EMD_R - 1) / EMD_R;      // at least one warp's worth of rows per CTA
+    ctas_per_item = c_cap / B;
+    if (ctas_per_item > want) ctas_per_item = want;
+    persistent = ctas_per_item >= 1;
+  }
+  if (persistent) {
+    cudaError_t me = cudaMemsetAsync(ticket, 0, (2 * (size_t)B + 1) * sizeof(unsigned int), s);
+    if (me != cudaSuccess) return (int)me;
+    EmdPersistParams q{};
+    q.xyz1 = xyz1_dev; q.xyz2 = xyz2_dev; q.remainL = remainL; q.remainR = remainR; q.ratioL = ratioL; q.ratioR = ratioR;
+    q.arrive = arrive; q.err = errw; q.B = B; q.n = n; q.m = m; q.ctas_per_item = ctas_per_item;
+    q.multiL = multiL; q.multiR = multiR;
+    for (int it = 0; it < EMD_LEVELS; ++it) q.lvl[it] = fp.lvl[it];
+    void* args[] = {&q};
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)emd_persistent_kernel, dim3((unsigned)(B * ctas_per_item)),
+                                                 dim3(EMD_THREADS), args, 0, s);
+    if (le == cudaSuccess) {
+      count_launch();
+      fp.err = errw;
+    } else {
+      (void)cudaGetLastError();            // e.g. cudaErrorCooperativeLaunchTooLarge under MPS: take the multi-launch path
+      persistent = false;
+    }
+  }
+  if (!persistent) {
   {
     // remainR = multiR (emd.cuh:24-25) and zero the arrival tickets
     const long tot = (long)B * m;
@@ -348,9 +499,6 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
   }
   const dim3 gridL((n + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
   const dim3 gridR((m + EMD_ROWS_PER_CTA - 1) / EMD_ROWS_PER_CTA, B);
-  EmdFinalParams fp{};
-  for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it);
-
   for (int it = 0; it < EMD_LEVELS; ++it) {
     if (it == 0) {
       EmdSweepParams p{};
@@ -381,6 +529,7 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
       count_launch();
       L3D_LAUNCH_CHECK();
     }
+  }
   }
   fp.xyz1 = xyz1_dev; fp.xyz2 = xyz2_dev; fp.ratioL = ratioL; fp.ratioR = ratioR;
   fp.match = match_dev; fp.partial = partial; fp.cost = cost_dev; fp.ticket = ticket;
