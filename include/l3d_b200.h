@@ -174,6 +174,12 @@ int l3d_chamfer_loss_backward(const float* xyz1_dev, const float* xyz2_dev, int 
                               const float* grad_loss_dev, float* gradxyz1_dev, float* gradxyz2_dev,
                               void* stream);
 
+/* Host-buffer convenience call (like l3d_knn_expansion_host): Chamfer loss of losses/chamfer_distance.py:34-43 and
+ * its gradients w.r.t. both clouds from HOST arrays xyz1_host [B,n,3], xyz2_host [B,m,3] -> loss_host [1],
+ * grad1_host [B,n,3], grad2_host [B,m,3] (both NULL = forward only).  Copies, two launches, copies back, one sync. */
+int l3d_chamfer_loss_fwd_bwd_host(const float* xyz1_host, const float* xyz2_host, int B, int n, int m,
+                                  float* loss_host, float* grad1_host, float* grad2_host);
+
 /* ---- pointnet2_cuda replacements (utils/lib/src/pointnet2_api.cpp:10-25) ------------------ */
 /* Same argument order, caller-allocated outputs and int32 indices as the reference wrappers. */
 
@@ -326,6 +332,39 @@ int l3d_debug_soft_correspondence_tiles(float* host_out);
 int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* tgt_emb_dev,
                                          const float* tgt_xyz_dev, int B, int D, int Ns, int Nt,
                                          float* src_corr_dev, float* scores_dev, void* stream);
+
+/* ---- RPMNet matching tail (models/rpmnet.py:130-254) ----------------------------------------
+ *
+ * l3d_feature_square_distance: square_distance (utils/ppfnet_util.py:29-48) on C-dimensional features, i.e.
+ * match_features(feat_src, feat_ref, 'l2') (rpmnet.py:130-154): src_dev [B,N,C], dst_dev [B,M,C] -> out_dev [B,N,M]
+ * = |s|^2 + |d|^2 - 2 s.d, the Gram matrix on tcgen05 (3xTF32).  With beta_dev / alpha_dev ([B] each, both or
+ * neither) the epilogue writes RPMNet's affinity -beta[b] * (dist - alpha[b]) (rpmnet.py:266-272) instead.
+ * ws_dev: l3d_feature_square_distance_ws_bytes(B, N, M) bytes.  Toleranced like any fp32 GEMM.
+ *
+ * l3d_sinkhorn: sinkhorn(log_alpha, n_iters, slack) (rpmnet.py:157-218, eps <= 0): log_alpha_dev [B,J,K] ->
+ * out_dev [B,J,K], the log of the (near) doubly stochastic matrix; slack != 0 adds the zero-padded slack row and
+ * column.  The input is never rewritten: row / column potentials + one finishing pass.
+ * ws_dev: l3d_sinkhorn_ws_bytes(B, J, K) bytes.
+ *
+ * l3d_rpm_match_tail: the same iterations fused with RPMNet.spam's tail (rpmnet.py:283-287):
+ * perm = exp(sinkhorn(affinity)) -> perm_out_dev [B,J,K] (optional), rowsum_out_dev [B,J] = sum_k perm (optional),
+ * weighted_out_dev [B,J,3] = perm @ xyz_ref / (rowsum + eps).  xyz_ref_dev [B,K,3].
+ *
+ * l3d_weighted_rigid_transform: compute_rigid_transform(a, b, weights) (rpmnet.py:221-254): a_dev, b_dev [B,M,3],
+ * w_dev [B,M] -> T_dev [B,3,4] = [R | t], weighted Kabsch with the reference's determinant rule (third right
+ * singular vector negated); eps = the reference's _EPS (1e-5, rpmnet.py:11) in w / (sum w + eps). */
+size_t l3d_feature_square_distance_ws_bytes(int B, int N, int M);
+int l3d_feature_square_distance(const float* src_dev, const float* dst_dev, int B, int N, int M, int C,
+                                const float* beta_dev, const float* alpha_dev, float* out_dev, void* ws_dev,
+                                void* stream);
+size_t l3d_sinkhorn_ws_bytes(int B, int J, int K);
+int l3d_sinkhorn(const float* log_alpha_dev, int B, int J, int K, int n_iters, int slack, float* out_dev,
+                 void* ws_dev, void* stream);
+int l3d_rpm_match_tail(const float* affinity_dev, const float* xyz_ref_dev, int B, int J, int K, int n_iters,
+                       int slack, float eps, float* perm_out_dev, float* weighted_out_dev, float* rowsum_out_dev,
+                       void* ws_dev, void* stream);
+int l3d_weighted_rigid_transform(const float* a_dev, const float* b_dev, const float* w_dev, int B, int M, float eps,
+                                 float* T_dev, void* stream);
 
 /* Testing hook: nonzero makes l3d_emd_forward take the multi-launch path (21 kernels) instead of the persistent
  * cooperative launch (all 20 sweeps in one kernel with per-item barriers).  Both give identical results. */

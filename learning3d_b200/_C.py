@@ -62,6 +62,13 @@ _SIGNATURES = {
     "l3d_debug_soft_correspondence_split": [_I],
     "l3d_debug_soft_correspondence_tiles": [_P],
     "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_chamfer_loss_fwd_bwd_host": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "l3d_feature_square_distance_ws_bytes": [_I, _I, _I],
+    "l3d_feature_square_distance": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "l3d_sinkhorn_ws_bytes": [_I, _I, _I],
+    "l3d_sinkhorn": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_rpm_match_tail": [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "l3d_weighted_rigid_transform": [_P, _P, _P, _I, _I, _F, _P, _P],
     "l3d_edgeconv_layer1": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
     "l3d_conv1x1_bn_relu_maxk": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
     "l3d_edgeconv_status": [],
@@ -81,6 +88,8 @@ _RESTYPE = {
     "l3d_chamfer_ws_bytes": ctypes.c_size_t,
     "l3d_knn_features_ws_bytes": ctypes.c_size_t,
     "l3d_emd_forward_ws_bytes": ctypes.c_size_t,
+    "l3d_feature_square_distance_ws_bytes": ctypes.c_size_t,
+    "l3d_sinkhorn_ws_bytes": ctypes.c_size_t,
     "l3d_emd_backward_ws_bytes": ctypes.c_size_t,
 }
 

@@ -15,6 +15,7 @@ What is replaced (reference file:line -> ours):
   utils/svd.py:13-59                 SVDHead.forward  (fused soft correspondences + batched Kabsch)
   models/dgcnn.py:25-49              DGCNN.forward    (eval mode: kNN graph + EdgeConv stack on tcgen05;
                                      training mode keeps the torch layers on the fused graph feature)
+  models/rpmnet.py:130-254           match_features, sinkhorn, compute_rigid_transform (RPMNet's matching tail)
   utils/lib/pointnet2_utils.py:8     the `pointnet2_cuda` extension module
 Nothing is copied from the reference; only attributes of the live package objects are swapped.
 """
@@ -56,6 +57,11 @@ def bind(pkg, edgeconv=True):
         from .models import dgcnn as our_dgcnn
         if hasattr(our_dgcnn, "dgcnn_forward"):
             _swap(rec, dg.DGCNN, "forward", our_dgcnn.dgcnn_forward)
+    rpm = sys.modules.get(pkg.__name__ + ".models.rpmnet")
+    if rpm is not None:
+        from .models import rpmnet as our_rpm
+        for n in ("match_features", "sinkhorn", "compute_rigid_transform"):
+            _swap(rec, rpm, n, getattr(our_rpm, n))
     pn2 = sys.modules.get(pkg.__name__ + ".utils.lib.pointnet2_utils")
     if pn2 is not None:
         from . import pointnet2_cuda

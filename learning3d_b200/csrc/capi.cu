@@ -118,3 +118,50 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   e = cudaStreamSynchronize(st[1]);
   return (int)e;
 }
+
+// Chamfer loss + both gradients from HOST buffers in one call (the "Chamfer fwd+bwd" half of the headline metric
+// for callers that are not PyTorch): H2D of the two clouds, the fused loss forward and backward launches with
+// dL/dloss = 1, D2H of the scalar and the two gradient clouds, one synchronisation.
+extern "C" int l3d_chamfer_loss_fwd_bwd_host(const float* xyz1_host, const float* xyz2_host, int B, int n, int m,
+                                             float* loss_host, float* grad1_host, float* grad2_host) {
+  if (!xyz1_host || !xyz2_host || !loss_host || B < 1 || n < 1 || m < 1) return L3D_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(l3d::g_host.mu);
+  const size_t b1 = (size_t)B * n * 3 * sizeof(float), b2 = (size_t)B * m * 3 * sizeof(float);
+  const size_t ws = l3d_chamfer_ws_bytes(B, n, m);
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  // out region: dist1 | dist2 | idx1 | idx2 | loss,one | ws | grad1 | grad2
+  const size_t o_d1 = 0, o_d2 = o_d1 + up((size_t)B * n * 4), o_i1 = o_d2 + up((size_t)B * m * 4),
+               o_i2 = o_i1 + up((size_t)B * n * 4), o_l = o_i2 + up((size_t)B * m * 4), o_ws = o_l + 256,
+               o_g1 = o_ws + up(ws), o_g2 = o_g1 + up(b1), o_end = o_g2 + up(b2);
+  int rc = l3d::g_host.ensure(up(b1) + up(b2), o_end);
+  if (rc) return rc;
+  cudaStream_t s = l3d::g_host.stream;
+  unsigned char* in = (unsigned char*)l3d::g_host.in;
+  unsigned char* out = (unsigned char*)l3d::g_host.out;
+  float* x1 = (float*)in;
+  float* x2 = (float*)(in + up(b1));
+  cudaError_t e = cudaMemcpyAsync(x1, xyz1_host, b1, cudaMemcpyHostToDevice, s);
+  if (e) return (int)e;
+  e = cudaMemcpyAsync(x2, xyz2_host, b2, cudaMemcpyHostToDevice, s);
+  if (e) return (int)e;
+  float* loss = (float*)(out + o_l);
+  static const float one = 1.0f;
+  e = cudaMemcpyAsync(loss + 1, &one, sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e) return (int)e;
+  rc = l3d_chamfer_loss_forward(x1, x2, B, n, m, (float*)(out + o_d1), (float*)(out + o_d2), (int32_t*)(out + o_i1),
+                                (int32_t*)(out + o_i2), loss, out + o_ws, s);
+  if (rc) return rc;
+  if (grad1_host && grad2_host) {
+    rc = l3d_chamfer_loss_backward(x1, x2, B, n, m, (const float*)(out + o_d1), (const float*)(out + o_d2),
+                                   (const int32_t*)(out + o_i1), (const int32_t*)(out + o_i2), loss + 1,
+                                   (float*)(out + o_g1), (float*)(out + o_g2), s);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(grad1_host, out + o_g1, b1, cudaMemcpyDeviceToHost, s);
+    if (e) return (int)e;
+    e = cudaMemcpyAsync(grad2_host, out + o_g2, b2, cudaMemcpyDeviceToHost, s);
+    if (e) return (int)e;
+  }
+  e = cudaMemcpyAsync(loss_host, loss, sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e) return (int)e;
+  return (int)cudaStreamSynchronize(s);
+}

@@ -319,6 +319,69 @@ __global__ void __launch_bounds__(SVDH_THREADS) svd_head_tail_bwd_kernel(
   }
 }
 
+// compute_rigid_transform (rpmnet.py:221-254): one CTA per item, fp64 sums.
+//   w~ = w / (sum w + eps);  ca = sum w~ a;  cb = sum w~ b;  cov = sum w~ (a - ca)(b - cb)^T
+//      = sum w~ a b^T - (2 - W) ca cb^T,  W = sum w~
+//   R = V U^T of cov = U S V^T (third column of V negated when det < 0), t = -R ca + cb
+constexpr int RT_THREADS = 256;
+__global__ void __launch_bounds__(RT_THREADS) weighted_rigid_kernel(const float* __restrict__ a, const float* __restrict__ bp,
+                                                                    const float* __restrict__ w, int M, float eps,
+                                                                    float* __restrict__ T) {
+  __shared__ double red[RT_THREADS / 32][16];
+  __shared__ double tot[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* A = a + (size_t)b * M * 3;
+  const float* Bq = bp + (size_t)b * M * 3;
+  const float* W = w + (size_t)b * M;
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int n = tid; n < M; n += RT_THREADS) {
+    const double wn = (double)W[n];
+    const double av[3] = {(double)A[n * 3], (double)A[n * 3 + 1], (double)A[n * 3 + 2]};
+    const double bv[3] = {(double)Bq[n * 3], (double)Bq[n * 3 + 1], (double)Bq[n * 3 + 2]};
+    acc[15] += wn;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { acc[i] += wn * av[i]; acc[3 + i] += wn * bv[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[6 + i * 3 + j] += wn * av[i] * bv[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(L3D_FULL_MASK, acc[i], o);
+    if (lane == 0) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < 16) {
+    double v = 0.0;
+    for (int q = 0; q < RT_THREADS / 32; ++q) v += red[q][tid];
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double inv = 1.0 / (tot[15] + (double)eps);      // weights_normalized = w / (sum w + eps)
+    const double Wn = tot[15] * inv;
+    double ca[3], cb[3], h[9];
+    float caf[3], cbf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ca[i] = tot[i] * inv; cb[i] = tot[3 + i] * inv; caf[i] = (float)ca[i]; cbf[i] = (float)cb[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) h[i * 3 + j] = tot[6 + i * 3 + j] * inv - (2.0 - Wn) * ca[i] * cb[j];
+    float R[9], t[3];
+    kabsch_from_H(h, caf, cbf, R, t, nullptr);
+    float* o = T + (size_t)b * 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      o[i * 4 + 0] = R[i * 3 + 0]; o[i * 4 + 1] = R[i * 3 + 1]; o[i * 4 + 2] = R[i * 3 + 2]; o[i * 4 + 3] = t[i];
+    }
+  }
+}
+
 }  // namespace l3d
 
 using namespace l3d;
@@ -354,6 +417,17 @@ extern "C" int l3d_svd_head_tail_backward(const float* src_dev, const float* src
   if (B == 0) return L3D_OK;
   svd_head_tail_bwd_kernel<<<B, SVDH_THREADS, 0, (cudaStream_t)stream>>>(
       src_dev, src_corr_dev, grad_R_dev, grad_t_dev, N, grad_src_dev, grad_src_corr_dev);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+extern "C" int l3d_weighted_rigid_transform(const float* a_dev, const float* b_dev, const float* w_dev, int B, int M,
+                                            float eps, float* T_dev, void* stream) {
+  if (B < 0 || M < 1) return L3D_ERR_INVALID;
+  if (B == 0) return L3D_OK;
+  if (!a_dev || !b_dev || !w_dev || !T_dev) return L3D_ERR_INVALID;
+  weighted_rigid_kernel<<<B, RT_THREADS, 0, (cudaStream_t)stream>>>(a_dev, b_dev, w_dev, M, eps, T_dev);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;

@@ -74,6 +74,10 @@ struct SoftCorrParams {
   const float* xx_a;      // [B, Ns]
   const float* xx_b;      // [B, Nt]
   float* keys;            // [B, Ns, Nt]   ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2
+  // EPI_SQDIST (feature-space square_distance / RPMNet affinity): optional per-item affinity transform
+  const float* aff_beta;  // [B] or null: out = -beta[b] * (dist - alpha[b])     (rpmnet.py:266-272)
+  const float* aff_alpha; // [B]
+  int kmajor;             // generic pipeline only: operands are [B, N, D] (channels contiguous) instead of [B, D, N]
   int* err;               // device error word (0 = ok)
   float* part;            // split target range only: partial softmax states [B, Ns, gridDim.z, 8]
   int tiles_per_split;    // target tiles handled by one CTA (all of them when gridDim.z == 1)
@@ -106,8 +110,23 @@ __device__ __forceinline__ uint32_t sc_swz(int r, int c) {
 
 // ---- generic producer helpers -------------------------------------------------------------------
 __device__ __forceinline__ void sc_load_row(const float* __restrict__ base, int D, int N, int d0,
-                                            int n, float (&v)[SC_GBK]) {
+                                            int n, float (&v)[SC_GBK], int kmajor = 0) {
   const bool nv = n < N;
+  if (kmajor) {
+    // [N, D] operand: the 32 channels of this row are contiguous (one 128-byte line per thread)
+    const float* p = base + (size_t)(nv ? n : 0) * D + d0;
+    if (nv && d0 + SC_GBK <= D && (D & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < SC_GBK / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+        v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < SC_GBK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + dd) : 0.f;
+    }
+    return;
+  }
   const float* p = base + (size_t)d0 * N + (nv ? n : 0);
 #pragma unroll
   for (int dd = 0; dd < SC_GBK; ++dd) v[dd] = (nv && d0 + dd < D) ? __ldg(p + (size_t)dd * N) : 0.f;
@@ -128,6 +147,18 @@ __device__ __forceinline__ void sc_store_row(uint32_t hi_tile, uint32_t lo_tile,
   }
 }
 
+constexpr int EPI_SQDIST = 2;        // square_distance on C-dim features (+ RPMNet's affinity) -> keys [B,Ns,Nt]
+// matrix-valued epilogues: what is written at (i, j) for the accumulator v = a_i . b_j
+template <int EPI>
+__device__ __forceinline__ float sc_matrix_value(float v, float xa_i, float xb_j, float beta, float alpha, bool aff) {
+  if (EPI == EPI_SQDIST) {
+    // dist = -2 * matmul(src, dst^T); dist += |src|^2; dist += |dst|^2      (ppfnet_util.py:45-47)
+    const float d = __fadd_rn(fmaf(-2.0f, v, xa_i), xb_j);
+    return aff ? __fmul_rn(-beta, __fsub_rn(d, alpha)) : d;               // -beta * (dist - alpha)
+  }
+  // pd = ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2  (model_common_utils.py:5-7, same association as knn.cu)
+  return __fsub_rn(fmaf(2.0f, v, -xb_j), xa_i);
+}
 constexpr int EPI_SOFTMAX_XYZ = 0;   // SVD head: online softmax, xyz-weighted sums  -> out [B,3,Ns]
 constexpr int EPI_KEYS = 1;          // feature-space kNN: negated expansion distances -> keys [B,Ns,Nt]
 
@@ -196,7 +227,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     const int i = i0 + tid;
     const float c = p.c;
     float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    const float xi = (EPI == EPI_KEYS && i < p.Ns) ? __ldg(p.xx_a + (size_t)b * p.Ns + i) : 0.f;
+    constexpr bool MATRIX = (EPI == EPI_KEYS || EPI == EPI_SQDIST);
+    const float xi = (MATRIX && i < p.Ns) ? __ldg(p.xx_a + (size_t)b * p.Ns + i) : 0.f;
+    const bool aff = (EPI == EPI_SQDIST) && p.aff_beta != nullptr;
+    const float a_beta = aff ? __ldg(p.aff_beta + b) : 0.f, a_alpha = aff ? __ldg(p.aff_alpha + b) : 0.f;
     bool ok = true;
     for (int jb = 0; jb < num_jb; ++jb) {
       const int a = jb & 1;
@@ -206,7 +240,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         const int j = j0 + jj;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < p.Nt) {
-          if (EPI == EPI_KEYS) {
+          if (MATRIX) {
             q.x = __ldg(p.xx_b + (size_t)b * p.Nt + j);
           } else {
             const float* t = p.tgt_xyz + (size_t)b * 3 * p.Nt + j;
@@ -229,9 +263,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             if (j0 + ch * 32 + e < p.Nt) p.dbg_scores[((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32 + e] = v[e];
         }
         if (ch * 32 >= nvalid) continue;
-        if (EPI == EPI_KEYS) {
-          // pd = ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2  (model_common_utils.py:5-7, same association as knn.cu);
-          // thread = row i: 32 consecutive floats of its key row, 16-byte stores when the row allows
+        if (MATRIX) {
+          // thread = row i: 32 consecutive floats of its row of the output matrix, 16-byte stores when the row allows
           const float4* xz = &sh->xyz[a][ch * 32];
           const int nv = min(32, nvalid - ch * 32);
           if (nv == 32 && (p.Nt & 3) == 0) {
@@ -241,10 +274,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               float4 o;
-              o.x = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
-              o.y = __fsub_rn(fmaf(2.0f, v[e + 1], -xz[e + 1].x), xi);
-              o.z = __fsub_rn(fmaf(2.0f, v[e + 2], -xz[e + 2].x), xi);
-              o.w = __fsub_rn(fmaf(2.0f, v[e + 3], -xz[e + 3].x), xi);
+              o.x = sc_matrix_value<EPI>(v[e], xi, xz[e].x, a_beta, a_alpha, aff);
+              o.y = sc_matrix_value<EPI>(v[e + 1], xi, xz[e + 1].x, a_beta, a_alpha, aff);
+              o.z = sc_matrix_value<EPI>(v[e + 2], xi, xz[e + 2].x, a_beta, a_alpha, aff);
+              o.w = sc_matrix_value<EPI>(v[e + 3], xi, xz[e + 3].x, a_beta, a_alpha, aff);
               *reinterpret_cast<float4*>(&tb[lane][e]) = o;
             }
             __syncwarp();
@@ -262,7 +295,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
             float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32;
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (e < nv) dst[e] = __fsub_rn(fmaf(2.0f, v[e], -xz[e].x), xi);
+              if (e < nv) dst[e] = sc_matrix_value<EPI>(v[e], xi, xz[e].x, a_beta, a_alpha, aff);
           }
           continue;
         }
@@ -308,7 +341,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
           o[0] = qnan; o[p.Ns] = qnan; o[2 * (size_t)p.Ns] = qnan;
         }
       }
-      if (EPI == EPI_KEYS && i < p.Ns) {
+      if ((EPI == EPI_KEYS || EPI == EPI_SQDIST) && i < p.Ns) {
         float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt;
         for (int j = 0; j < p.Nt; ++j) dst[j] = qnan;
       }
@@ -368,8 +401,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       float va[SC_GBK], vb[SC_GBK];
       for (int it = 0; it < total; ++it) {
         const int jb = it / num_kb, kb = it - jb * num_kb;
-        sc_load_row(A, p.D, p.Ns, kb * SC_BK, i0 + r, va);
-        sc_load_row(Bm, p.D, p.Nt, kb * SC_BK, (jb0 + jb) * SC_BN + r, vb);
+        sc_load_row(A, p.D, p.Ns, kb * SC_BK, i0 + r, va, p.kmajor);
+        sc_load_row(Bm, p.D, p.Nt, kb * SC_BK, (jb0 + jb) * SC_BN + r, vb, p.kmajor);
         const int s = it % SC_STAGES;
         const uint32_t n = (uint32_t)(it / SC_STAGES);
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
@@ -538,7 +571,7 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   dim3 grid((p.Ns + SC_BM - 1) / SC_BM, p.B);
 
   // TMA needs 16-byte global strides and bases
-  bool tma = g_softcorr_force_generic != 1 && (p.Ns % 4 == 0) && (p.Nt % 4 == 0) &&
+  bool tma = g_softcorr_force_generic != 1 && !p.kmajor && (p.Ns % 4 == 0) && (p.Nt % 4 == 0) &&
              (((uintptr_t)p.src_emb | (uintptr_t)p.tgt_emb) & 15) == 0;
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
@@ -664,6 +697,47 @@ static __global__ void sqnorm_kernel(const float* __restrict__ x, int B, int C, 
     for (int k = 1; k < 8; ++k) s = __fadd_rn(s, part[k][ln]);
     xx[t] = s;
   }
+}
+
+// |x_n|^2 for [B, N, C] rows (channels contiguous): torch.sum(x ** 2, dim=-1), accumulated in channel order
+static __global__ void sqnorm_rows_kernel(const float* __restrict__ x, long rows, int C, float* __restrict__ xx) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows) return;
+  const float* p = x + (size_t)t * C;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = __fadd_rn(acc, __fmul_rn(p[c], p[c]));
+  xx[t] = acc;
+}
+
+extern "C" size_t l3d_feature_square_distance_ws_bytes(int B, int N, int M) {
+  if (B < 1 || N < 1 || M < 1) return 0;
+  return sizeof(float) * (size_t)B * ((size_t)N + M);
+}
+
+// square_distance(src, dst) of utils/ppfnet_util.py:29-48 / model_common_utils.py:19-38 for C-dimensional features
+// (RPMNet's match_features, models/rpmnet.py:130-154): src [B,N,C], dst [B,M,C] -> out [B,N,M], Gram matrix on
+// tcgen05 (3xTF32).  With beta/alpha ([B] each) the epilogue writes RPMNet's affinity -beta*(dist - alpha) instead.
+extern "C" int l3d_feature_square_distance(const float* src_dev, const float* dst_dev, int B, int N, int M, int C,
+                                           const float* beta_dev, const float* alpha_dev, float* out_dev,
+                                           void* ws_dev, void* stream) {
+  if (B < 0 || N < 0 || M < 0 || C < 1) return L3D_ERR_INVALID;
+  if (B == 0 || N == 0 || M == 0) return L3D_OK;
+  if (!src_dev || !dst_dev || !out_dev || !ws_dev || ((beta_dev == nullptr) != (alpha_dev == nullptr))) return L3D_ERR_INVALID;
+  float* xa = reinterpret_cast<float*>(ws_dev);
+  float* xb = xa + (size_t)B * N;
+  const long ra = (long)B * N, rb = (long)B * M;
+  sqnorm_rows_kernel<<<(unsigned)((ra + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src_dev, ra, C, xa);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  sqnorm_rows_kernel<<<(unsigned)((rb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst_dev, rb, C, xb);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = src_dev; p.tgt_emb = dst_dev; p.xx_a = xa; p.xx_b = xb; p.keys = out_dev;
+  p.aff_beta = beta_dev; p.aff_alpha = alpha_dev; p.kmajor = 1;
+  p.B = B; p.D = C; p.Ns = N; p.Nt = M;
+  return sc_launch<EPI_SQDIST>(p, stream);
 }
 
 static size_t knn_features_keys_bytes(int B, int N) {

@@ -24,9 +24,35 @@ def _xyz(t, name):
     return t
 
 
+def feature_square_distance(src, dst, beta=None, alpha=None):
+    """square_distance(src [B,N,C], dst [B,M,C]) -> [B,N,M] on the tensor cores (any C); with beta/alpha [B] the
+    epilogue returns RPMNet's affinity -beta * (dist - alpha) instead."""
+    src, dst = _C.require_cuda(src, "src"), _C.require_cuda(dst, "dst")
+    B, N, C = src.shape
+    M = dst.shape[1]
+    if dst.shape[0] != B or dst.shape[2] != C:
+        raise ValueError("square_distance: inconsistent shapes %s %s" % (tuple(src.shape), tuple(dst.shape)))
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    lib = _C.lib()
+    if beta is not None:
+        beta = _C.require_cuda(beta.reshape(B), "beta")
+        alpha = _C.require_cuda(alpha.reshape(B) if isinstance(alpha, torch.Tensor)
+                                else torch.full((B,), float(alpha), device=src.device), "alpha")
+    with _C.on_device(src.device):
+        ws = torch.empty(max(int(lib.l3d_feature_square_distance_ws_bytes(B, N, M)), 16), dtype=torch.uint8,
+                         device=src.device)
+        _C.check(lib.l3d_feature_square_distance(_C.ptr(src), _C.ptr(dst), B, N, M, C, _C.ptr(beta), _C.ptr(alpha),
+                                                 _C.ptr(out), _C.ptr(ws), _C.stream()), "square_distance")
+    return out
+
+
+
 def square_distance(src, dst):
-    """model_common_utils.py:19-38 — [B,N,3], [B,M,3] -> [B,N,M] expansion-form squared distance."""
+    """model_common_utils.py:19-38 — [B,N,C], [B,M,C] -> [B,N,M] expansion-form squared distance.  C = 3 (clouds):
+    bit-exact SIMT kernel; any other C (RPMNet's 96-d features): Gram matrix on the tensor cores (toleranced)."""
     _no_grad("square_distance", src, dst)
+    if src.dim() == 3 and src.size(2) != 3:
+        return feature_square_distance(src, dst)
     src, dst = _xyz(src, "src"), _xyz(dst, "dst")
     B, N, _ = src.shape
     M = dst.shape[1]

@@ -187,12 +187,47 @@ def gen_dcp():
     save("dcp_small", **arrays)
 
 
+def gen_rpm():
+    """RPMNet's matching tail run by the REAL reference (models/rpmnet.py:130-254): match_features on 96-d
+    features, the affinity of RPMNet.compute_affinity (:266-272), sinkhorn with and without slack, the weighted
+    template of RPMNet.spam (:283-287) and compute_rigid_transform (incl. one reflected item)."""
+    from learning3d.models import rpmnet as R
+    torch.manual_seed(99)
+    B, J, K, C = 3, 70, 90, 96
+    fs = torch.randn(B, J, C) * 0.3
+    fr = torch.cat([fs[:, :60] + 0.05 * torch.randn(B, 60, C), torch.randn(B, K - 60, C) * 0.3], dim=1)
+    dist = R.match_features(fs, fr)
+    beta = torch.tensor([1.5, 4.0, 0.7]); alpha = torch.tensor([0.5, 1.0, 2.0])
+    aff = -beta[:, None, None] * (dist - alpha[:, None, None])
+    log_perm = R.sinkhorn(aff, n_iters=5, slack=True)
+    log_noslack = R.sinkhorn(aff, n_iters=3, slack=False)
+    xyz_ref = torch.rand(B, K, 3) - 0.5
+    xyz_src = torch.rand(B, J, 3) - 0.5
+    perm = torch.exp(log_perm)
+    weighted = perm @ xyz_ref / (torch.sum(perm, dim=2, keepdim=True) + R._EPS)
+    w = torch.sum(perm, dim=2)
+    T = R.compute_rigid_transform(xyz_src, weighted, weights=w)
+    # a second, well conditioned rigid-transform case with a reflection: b = mirrored a
+    a2 = torch.rand(4, 200, 3) - 0.5
+    rot = torch.linalg.qr(torch.randn(4, 3, 3))[0]
+    rot[2:] = rot[2:] * torch.tensor([1.0, 1.0, -1.0])          # items 2, 3: improper (det < 0) maps
+    b2 = a2 @ rot.transpose(1, 2) + torch.rand(4, 1, 3)
+    w2 = torch.rand(4, 200)
+    T2 = R.compute_rigid_transform(a2, b2, w2)
+    save("rpm_tail", feat_src=fs.numpy(), feat_ref=fr.numpy(), dist=dist.numpy(), beta=beta.numpy(), alpha=alpha.numpy(),
+         affinity=aff.numpy(), log_perm=log_perm.numpy(), log_noslack=log_noslack.numpy(), xyz_ref=xyz_ref.numpy(),
+         xyz_src=xyz_src.numpy(), perm=perm.numpy(), weighted=weighted.numpy(), rowsum=w.numpy(), T=T.numpy(),
+         a2=a2.numpy(), b2=b2.numpy(), w2=w2.numpy(), T2=T2.numpy())
+
+
 if __name__ == "__main__":
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     os.environ.setdefault("TORCH_EXTENSIONS_DIR", tempfile.mkdtemp(prefix="l3dref_ext_"))
     os.environ["CC"] = "/usr/bin/gcc"; os.environ["CXX"] = "/usr/bin/g++"
     import_reference()
-    which = sys.argv[1:] or ["knn", "chamfer", "group", "svd", "dcp"]
+    which = sys.argv[1:] or ["knn", "chamfer", "group", "svd", "dcp", "rpm"]
+    if "rpm" in which:
+        gen_rpm()
     if "knn" in which:
         gen_knn()
     if "chamfer" in which:
