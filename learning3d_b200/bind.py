@@ -13,6 +13,7 @@ What is replaced (reference file:line -> ours):
                                      farthest_point_sample, knn_point, query_ball_point (and the names
                                      re-exported by utils/__init__.py and imported into models/*.py)
   utils/svd.py:13-59                 SVDHead.forward  (fused soft correspondences + batched Kabsch)
+  utils/transformer.py:255-263       Transformer.forward (eval: linear layers, attention, LayerNorm on tcgen05)
   models/dgcnn.py:25-49              DGCNN.forward    (eval mode: kNN graph + EdgeConv stack on tcgen05;
                                      training mode keeps the torch layers on the fused graph feature)
   models/rpmnet.py:130-254           match_features, sinkhorn, compute_rigid_transform (RPMNet's matching tail)
@@ -57,6 +58,13 @@ def bind(pkg, edgeconv=True):
         from .models import dgcnn as our_dgcnn
         if hasattr(our_dgcnn, "dgcnn_forward"):
             _swap(rec, dg.DGCNN, "forward", our_dgcnn.dgcnn_forward)
+    tr = sys.modules.get(pkg.__name__ + ".utils.transformer")
+    if tr is not None and hasattr(tr, "Transformer"):
+        from .utils.transformer_fused import transformer_forward
+        if not hasattr(tr.Transformer, "_l3d_torch_forward"):
+            tr.Transformer._l3d_torch_forward = tr.Transformer.forward      # kept for training / autograd
+            rec.append((tr.Transformer, "_l3d_torch_forward", None))
+        _swap(rec, tr.Transformer, "forward", transformer_forward)
     rpm = sys.modules.get(pkg.__name__ + ".models.rpmnet")
     if rpm is not None:
         from .models import rpmnet as our_rpm
@@ -73,5 +81,8 @@ def bind(pkg, edgeconv=True):
 def unbind(pkg):
     """Undo bind(pkg)."""
     for obj, attr, old in reversed(_SAVED.pop(id(pkg), [])):
-        setattr(obj, attr, old)
+        if old is None:
+            delattr(obj, attr)
+        else:
+            setattr(obj, attr, old)
     return pkg

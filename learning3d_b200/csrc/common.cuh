@@ -70,6 +70,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): two independent IEEE fp32 lanes per instruction, each
+// rounded exactly like the scalar op, so a key computed in a packed lane is bit-identical to knn_key<>.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 // ---- ordering used by every selection kernel ---------------------------------------
 // "better" = larger key first; equal keys -> lower index first.  All kNN flavours map
 // their distance to a key whose LARGEST values are the nearest neighbours, so one
@@ -245,6 +270,29 @@ __device__ __forceinline__ float warp_sort32_keys_desc(float v, int lane) {
     }
   }
   return v;
+}
+
+// R independent keys-only sorts, interleaved stage by stage (their shuffle latencies overlap)
+template <int R>
+__device__ __forceinline__ void warp_sort32_keys_desc_x(float (&v)[R], int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+    const bool kb = (lane & (k2 >> 1)) == 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float o = __shfl_xor_sync(L3D_FULL_MASK, v[r], k2 - 1);
+      v[r] = kb ? fmaxf(v[r], o) : fminf(v[r], o);
+    }
+#pragma unroll
+    for (int j = k2 >> 2; j > 0; j >>= 1) {
+      const bool kj = (lane & j) == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float o = __shfl_xor_sync(L3D_FULL_MASK, v[r], j);
+        v[r] = kj ? fmaxf(v[r], o) : fminf(v[r], o);
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ int warp_inclusive_scan(int x, int lane) {

@@ -36,9 +36,11 @@
 
 namespace l3d {
 
-constexpr int EC_EPI_THREADS = 128;
+constexpr int EC_EPI_THREADS = 128;   // one epilogue group = 4 warps = the 128 TMEM lanes of an accumulator
+constexpr int EC_EPI_GROUPS = 2;      // group g drains accumulator g (even / odd tiles)
 constexpr int EC_SPLIT_THREADS = 128;
-constexpr int EC_THREADS = EC_EPI_THREADS + EC_SPLIT_THREADS + 64;   // + MMA warp + TMA warp
+// warps 0-3 epilogue group 0 | 4-7 splitters | 8 MMA issuer | 9 TMA issuer | 10-13 epilogue group 1
+constexpr int EC_THREADS = EC_EPI_THREADS + EC_SPLIT_THREADS + 64 + EC_EPI_THREADS;
 constexpr int EC_BN = 256;           // positions per MMA (UMMA N)
 constexpr int EC_BK = 16;            // input channels per pipeline stage
 constexpr int EC_MAX_GROUPS = 16;    // pooled groups (points) per tile
@@ -67,6 +69,8 @@ struct EdgeParams {
   int G, TS;             // positions per pooled group; tile stride in positions (multiple of G, <= 256)
   int tiles_per_item, m_blocks, units;
   int relu;
+  const float* residual; // optional [B, M, P]: added after the activation (transformer sublayers: x + f(norm(x)))
+  int w_heads;           // 0: one weight matrix for every item.  h > 0: item b uses rows (b % h)*M.. of weight batch b / h
 };
 
 struct EdgeShared {
@@ -76,9 +80,14 @@ struct EdgeShared {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  alignas(16) float tbuf[EC_EPI_THREADS / 32][32][36];   // per-warp 32 x 32 transpose tile for the h_out stores
-  float pool[EC_EPI_THREADS][EC_MAX_GROUPS + 1];         // thread-private pooled values of the current tile
+  // per-epilogue-warp 32 x 32 transpose tile for the h_out stores, XOR-swizzled 16-byte chunks (no padding);
+  // the generic-G pooling path keeps a thread's <= 16 pooled values of the current tile in its own row
+  alignas(16) float tbuf[EC_EPI_GROUPS * EC_EPI_THREADS / 32][32][32];
 };
+// tile stride (owned positions per tile) for a group size G: whole groups only, at most EC_MAX_GROUPS of them
+__host__ __device__ constexpr int edge_tile_stride(int G) {
+  return G * ((EC_BN / G) < EC_MAX_GROUPS ? (EC_BN / G) : EC_MAX_GROUPS);
+}
 
 __device__ int g_edgeconv_error = 0;
 
@@ -93,7 +102,8 @@ __device__ __forceinline__ EdgeUnit edge_unit(const EdgeParams& p, int u, int ct
   return r;
 }
 
-template <int CTAS>
+// GT: compile-time pooling group size for the epilogue's fast path (20 = DGCNN's k; 1 = the generic path only)
+template <int CTAS, int GT>
 __global__ void __launch_bounds__(EC_THREADS, 1)
 edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_x) {
@@ -139,14 +149,19 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
 
-  if (warp < 4) {
+  if (warp < 4 || warp >= 10) {
     // ------------------------------------------------ epilogue: BN + ReLU, max over groups of G positions, stores
+    // two groups of four warps: group g drains accumulator g, i.e. the tiles t = g, g+2, ... of this CTA
+    const int grp = warp < 4 ? 0 : 1;
+    const int w4 = warp & 3;                        // TMEM lane quarter this warp may read (warp id % 4)
+    const int row = w4 * 32 + lane;                 // accumulator lane = output channel within the block
+    float(*tb)[32] = sh->tbuf[grp * 4 + w4];
     const float qnan = __int_as_float(0x7fc00000);
     bool ok = true;
-    for (int t = 0; t < my_tiles; ++t) {
+    for (int t = grp; t < my_tiles; t += EC_EPI_GROUPS) {
       const EdgeUnit un = edge_unit(p, cluster_id + t * n_clusters, CTAS, crank);
-      const int a = t & 1;
-      const int c = un.m0 + tid;                    // this thread's output channel
+      const int a = grp;
+      const int c = un.m0 + row;                    // this thread's output channel
       const bool vrow = c < p.M;
       const int nvalid = min(p.TS, p.P - un.j0);    // positions this tile owns
       const bool vec = ((p.P & 3) == 0) && ((un.j0 & 3) == 0) && ((nvalid & 3) == 0);
@@ -171,64 +186,112 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
       }
       __syncwarp();
       tc_fence_after();
-      const float s = vrow ? __ldg(p.scale + c) : 0.f, sf = vrow ? __ldg(p.shift + c) : 0.f;
-      float gm = -INFINITY;
-      int cnt = 0, gi = 0;
-#pragma unroll 1
-      for (int ch = 0; ch < EC_BN / 32; ++ch) {
-        if (ch * 32 >= nvalid) break;
-        float v[32];
-        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * EC_BN + ch * 32), v);
-        const int nv = min(32, nvalid - ch * 32);
+      const float s = vrow ? (p.scale ? __ldg(p.scale + c) : 1.f) : 0.f, sf = (vrow && p.shift) ? __ldg(p.shift + c) : 0.f;
+      const uint32_t tacc = tmem + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(a * EC_BN);
+      float* pdst = p.pool_out ? p.pool_out + (size_t)un.b * p.pool_bstride + (size_t)(p.pool_coff + c) * p.pool_n + un.j0 / p.G
+                               : nullptr;
+      // one 32-column chunk: folded BN (+ ReLU) in place, and the transposed, coalesced h_out store
+      auto chunk = [&](int ch, float (&v)[32], int nv) {
+        tc_ld32(tacc + (uint32_t)(ch * 32), v);
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const float y = fmaf(v[e], s, sf);
           v[e] = p.relu ? fmaxf(y, 0.f) : y;
         }
-        if (p.h_out) {
-          if (vec) {
-            // transpose the warp's 32 x 32 block through shared memory: every store instruction then writes
-            // four (partly) complete 128-byte lines instead of 16-byte pieces of 32 different rows
-            float(*tb)[36] = sh->tbuf[warp];
+        if (!p.h_out) return;
+        if (vec) {
+          // transpose the warp's 32 x 32 block through shared memory (16-byte chunk q of row r lives at chunk
+          // q ^ (r & 7): conflict-free both ways): every store instruction then writes four 128-byte lines
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(&tb[lane][e]) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            __syncwarp();
-            const int rr = lane >> 3, cc = (lane & 7) * 4;
-            const int cbase = un.m0 + warp * 32;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(&tb[lane][((q ^ (lane & 7)) << 2)]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const int rr = lane >> 3, cq = lane & 7;
+          const int cbase = un.m0 + w4 * 32;
 #pragma unroll
-            for (int r = 0; r < 32; r += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(&tb[r + rr][cc]);
-              const int cr = cbase + r + rr;
-              if (cr < p.M && cc < nv)
-                *reinterpret_cast<float4*>(p.h_out + ((size_t)un.b * p.M + cr) * p.P + un.j0 + ch * 32 + cc) = o;
+          for (int r = 0; r < 32; r += 4) {
+            float4 o = *reinterpret_cast<const float4*>(&tb[r + rr][((cq ^ ((r + rr) & 7)) << 2)]);
+            const int cr = cbase + r + rr;
+            if (cr < p.M && cq * 4 < nv) {
+              const size_t off = ((size_t)un.b * p.M + cr) * p.P + un.j0 + ch * 32 + cq * 4;
+              if (p.residual) {
+                const float4 rz = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+                o.x += rz.x; o.y += rz.y; o.z += rz.z; o.w += rz.w;
+              }
+              *reinterpret_cast<float4*>(p.h_out + off) = o;
             }
-            __syncwarp();
-          } else if (vrow) {
-            float* dst = p.h_out + ((size_t)un.b * p.M + c) * p.P + un.j0 + ch * 32;
+          }
+          __syncwarp();
+        } else if (vrow) {
+          const size_t off = ((size_t)un.b * p.M + c) * p.P + un.j0 + ch * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nv) p.h_out[off + e] = p.residual ? v[e] + __ldg(p.residual + off + e) : v[e];
+        }
+      };
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);
+          else mbar_arrive(&sh->acc_empty[a]);
+        }
+      };
+      if (GT > 1 && nvalid == edge_tile_stride(GT > 1 ? GT : 2)) {
+        // full tile, compile-time group size: every index below is static after unrolling — the pooled maxima
+        // live in registers, the max chains of different groups are independent (ILP), no branches
+        constexpr int TSS = edge_tile_stride(GT > 1 ? GT : 2);
+        constexpr int NG = TSS / (GT > 1 ? GT : 2);
+        float pool[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) pool[g] = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < (TSS + 31) / 32; ++ch) {
+          float v[32];
+          chunk(ch, v, (TSS - ch * 32) < 32 ? (TSS - ch * 32) : 32);
+          if (pdst) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (e < nv) dst[e] = v[e];
+              if (ch * 32 + e < TSS) pool[(ch * 32 + e) / (GT > 1 ? GT : 2)] = fmaxf(pool[(ch * 32 + e) / (GT > 1 ? GT : 2)], v[e]);
           }
         }
-        if (p.pool_out) {
+        release();
+        if (pdst && vrow) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (e < nv) {
-              gm = fmaxf(gm, v[e]);
-              if (++cnt == p.G) { sh->pool[tid][gi++] = gm; gm = -INFINITY; cnt = 0; }
+          for (int g = 0; g < NG; ++g) pdst[g] = pool[g];
+        }
+      } else {
+        // generic: run-time group size and / or a short last tile
+        float gm = -INFINITY;
+        int cnt = 0, gi = 0;
+        float pl[EC_MAX_GROUPS];
+#pragma unroll
+        for (int g = 0; g < EC_MAX_GROUPS; ++g) pl[g] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < EC_BN / 32; ++ch) {
+          if (ch * 32 >= nvalid) break;
+          float v[32];
+          const int nv = min(32, nvalid - ch * 32);
+          chunk(ch, v, nv);
+          if (pdst) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (e < nv) {
+                gm = fmaxf(gm, v[e]);
+                if (++cnt == p.G) {
+#pragma unroll
+                  for (int g = 0; g < EC_MAX_GROUPS; ++g) if (g == gi) pl[g] = gm;
+                  ++gi; gm = -INFINITY; cnt = 0;
+                }
+              }
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(&sh->acc_empty[a], 0);
-        else mbar_arrive(&sh->acc_empty[a]);
-      }
-      if (p.pool_out && vrow) {
-        float* dst = p.pool_out + (size_t)un.b * p.pool_bstride + (size_t)(p.pool_coff + c) * p.pool_n + un.j0 / p.G;
-        for (int g = 0; g < gi; ++g) dst[g] = sh->pool[tid][g];
+        release();
+        if (pdst && vrow) {
+#pragma unroll
+          for (int g = 0; g < EC_MAX_GROUPS; ++g) if (g < gi) pdst[g] = pl[g];
+        }
       }
     }
   } else if (warp < 8) {
@@ -324,9 +387,10 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
         if (lane == 0) {
           const uint32_t st = tiles_s + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&sh->tma_full[s], A_TILE + B_TILE);
+          const int wm0 = un.m0 + (p.w_heads ? (un.b % p.w_heads) * p.M : 0), wb = p.w_heads ? un.b / p.w_heads : 0;
 #pragma unroll
           for (int q = 0; q < SC_BM / 32; ++q)
-            tma_load_3d(st + q * Cfg::ATOM, &tmap_w, un.m0 + 32 * q, kb * EC_BK, 0, &sh->tma_full[s]);
+            tma_load_3d(st + q * Cfg::ATOM, &tmap_w, wm0 + 32 * q, kb * EC_BK, wb, &sh->tma_full[s]);
 #pragma unroll
           for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
             tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_x, un.j0 + (int)crank * Cfg::BN_LOCAL + 32 * q, kb * EC_BK,
@@ -467,13 +531,14 @@ extern "C" int l3d_edgeconv_layer1(const float* x_dev, const int64_t* idx_dev, c
 
 // relu(scale * (W . X) + shift) for X [B, K, P], W^T [K, M]; optional full output h_out [B, M, P] and optional max
 // over every group of G consecutive positions -> pool_out[b*pool_bstride + (pool_coff + c)*(P/G) + n].
-extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const float* scale_dev,
-                                        const float* shift_dev, int B, int M, int K, int P, int G, int relu,
-                                        float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
-                                        void* stream) {
+static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float* scale_dev, const float* shift_dev,
+                            const float* residual_dev, int w_heads, int B, int M, int K, int P, int G, int relu,
+                            float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
+                            void* stream) {
   if (B < 0 || M < 1 || K < 1 || P < 1 || G < 1) return L3D_ERR_INVALID;
   if (B == 0) return L3D_OK;
-  if (!wt_dev || !x_dev || !scale_dev || !shift_dev || (!h_out_dev && !pool_out_dev)) return L3D_ERR_INVALID;
+  if (!wt_dev || !x_dev || (!h_out_dev && !pool_out_dev) || w_heads < 0) return L3D_ERR_INVALID;
+  if (w_heads > 0 && (M != SC_BM || B % w_heads != 0)) return L3D_ERR_UNSUPPORTED;   // one 128-row block per head
   if (pool_out_dev && (P % G != 0 || G > EC_BN)) return L3D_ERR_INVALID;
   // TMA: 16-byte global strides and bases
   if ((P & 3) || (M & 3) || ((((uintptr_t)wt_dev) | ((uintptr_t)x_dev)) & 15)) return L3D_ERR_UNSUPPORTED;
@@ -483,10 +548,9 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
   p.scale = scale_dev; p.shift = shift_dev; p.h_out = h_out_dev; p.pool_out = pool_out_dev;
   p.pool_bstride = (long)pool_bstride; p.pool_coff = pool_coff;
   p.B = B; p.M = M; p.K = K; p.P = P; p.G = G; p.relu = relu;
+  p.residual = residual_dev; p.w_heads = w_heads;
   if (pool_out_dev) {
-    int groups = EC_BN / G;
-    if (groups > EC_MAX_GROUPS) groups = EC_MAX_GROUPS;
-    p.TS = groups * G;
+    p.TS = edge_tile_stride(G);
     p.pool_n = P / G;
   } else {
     p.TS = EC_BN;
@@ -506,9 +570,13 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
     static uint64_t done_mask = 0;
     std::lock_guard<std::mutex> lock(mu);
     if (dev >= 64 || !(done_mask >> dev & 1)) {
-      cudaError_t e = cudaFuncSetAttribute(edge_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
+      cudaError_t e = cudaFuncSetAttribute(edge_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(edge_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
+      e = cudaFuncSetAttribute(edge_gemm_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(edge_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(edge_gemm_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
       if (e != cudaSuccess) return (int)e;
       if (dev < 64) done_mask |= (uint64_t)1 << dev;
     }
@@ -520,9 +588,12 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
 
   CUtensorMap mw, mx;
   memset(&mw, 0, sizeof(mw)); memset(&mx, 0, sizeof(mx));
-  if (!make_dn_tmap(&mw, wt_dev, 1, K, M, EC_BK) || !make_dn_tmap(&mx, x_dev, B, K, P, EC_BK)) return L3D_ERR_UNSUPPORTED;
+  // weights: [K, M] shared by every item, or (w_heads > 0) [B / w_heads, K, w_heads * M] with one head per item
+  const bool wok = w_heads ? make_dn_tmap(&mw, wt_dev, B / w_heads, K, w_heads * M, EC_BK) : make_dn_tmap(&mw, wt_dev, 1, K, M, EC_BK);
+  if (!wok || !make_dn_tmap(&mx, x_dev, B, K, P, EC_BK)) return L3D_ERR_UNSUPPORTED;
 
   const int sms = edge_sm_count(dev);
+  const bool fast20 = pool_out_dev != nullptr && G == 20 && p.TS == edge_tile_stride(20);
   if (pair) {
     long clusters = sms / 2;
     if (clusters > units) clusters = units;
@@ -535,16 +606,41 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2>, p, mw, mx);
+    // DGCNN's k = 20 has a compile-time epilogue (static group boundaries); every other G runs the generic one
+    cudaError_t le = fast20 ? cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 20>, p, mw, mx)
+                            : cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 1>, p, mw, mx);
     if (le != cudaSuccess) return (int)le;
   } else {
     long grid = sms;
     if (grid > units) grid = units;
-    edge_gemm_kernel<1><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
+    if (fast20) edge_gemm_kernel<1, 20><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
+    else edge_gemm_kernel<1, 1><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
   }
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;
+}
+
+extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const float* scale_dev,
+                                        const float* shift_dev, int B, int M, int K, int P, int G, int relu,
+                                        float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
+                                        void* stream) {
+  if (!scale_dev) return L3D_ERR_INVALID;
+  return edge_gemm_launch(wt_dev, x_dev, scale_dev, shift_dev, nullptr, 0, B, M, K, P, G, relu, h_out_dev, pool_out_dev,
+                          pool_bstride, pool_coff, stream);
+}
+
+// Channel-major linear layer  out[b, m, p] = act(sum_k wt[.., k, m] x[b, k, p] + bias[m]) (+ residual[b, m, p])
+// on the same tcgen05 pipeline (the transformer's nn.Linear layers with activations kept as [B, d_model, N]).
+// w_heads = 0: wt_dev [K, M] shared by all items.  w_heads = h > 0 ("one head per item", the P.V product of
+// attention): x_dev has B = batch*h items, wt_dev is [batch, K, h*M] and item b uses columns (b % h)*M.. of weight
+// batch b / h; M must be 128.
+extern "C" int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev,
+                             int B, int M, int K, int P, int relu, int w_heads, float* out_dev, void* stream) {
+  if (!out_dev) return L3D_ERR_INVALID;
+  if ((M * w_heads) & 3) return L3D_ERR_UNSUPPORTED;
+  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, residual_dev, w_heads, B, M, K, P, 1, relu, out_dev, nullptr,
+                          0, 0, stream);
 }
 
 // Synchronises the device and returns (then clears) the pipeline error word of l3d_conv1x1_bn_relu_maxk:

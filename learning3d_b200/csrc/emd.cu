@@ -24,13 +24,16 @@
 #include "launch_count.h"
 
 #include <algorithm>
+#include <mutex>
 
 namespace l3d {
 
 constexpr int EMD_THREADS = 256;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
-constexpr int EMD_R = 4;                         // rows per warp
-constexpr int EMD_ROWS_PER_CTA = EMD_WARPS * EMD_R;
+constexpr int EMD_R = 4;                         // rows per warp (two packed-f32x2 row pairs)
+constexpr int EMD_CSPLIT = 2;                    // warps sharing a row group, each sweeping every 2nd 32-column block
+constexpr int EMD_RGROUPS = EMD_WARPS / EMD_CSPLIT;
+constexpr int EMD_ROWS_PER_CTA = EMD_RGROUPS * EMD_R;
 constexpr int EMD_CHUNK = 1024;                  // columns staged per chunk
 constexpr int EMD_LEVELS = 10;                   // j = 7 .. -2 (emd.cuh:27)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -81,24 +84,31 @@ struct EmdSweepParams {
   int init;                // ph1 of the first level: remain = multi
 };
 
-// One weighted row sweep for the rows [row_begin, row_end) of batch item b, executed by one CTA (8 warps x 4 rows
-// per pass).  COHERENT: the column weights / row state were written by OTHER CTAs of the same launch (persistent
-// kernel, after a per-item barrier), so they are read with ld.global.cg (L2) instead of through L1.
+// One weighted row sweep for the rows [row_begin, row_end) of batch item b, executed by one CTA: 4 row groups of 4
+// rows, each shared by 2 warps that take alternate 32-column blocks (twice the warps per row = twice the latency
+// hiding; their partial sums meet in shared memory).  The 4 rows of a warp are two packed-f32x2 pairs: every FADD /
+// FMUL / FFMA below processes two rows (sm_100 FADD2 / FMUL2 / FFMA2, per-lane IEEE rounding = the scalar results).
+// COHERENT: the column weights / row state were written by OTHER CTAs of the same launch (persistent kernel, after
+// a per-item barrier), so they are read with ld.global.cg (L2) instead of through L1.
 template <bool FUSED, bool COHERENT>
 __device__ __forceinline__ void emd_sweep_rows(const EmdSweepParams& p, int b, int row_begin, int row_end,
-                                               float4* s_col, float* s_vb) {
+                                               float4* s_col, float* s_vb, float (*s_part)[EMD_RGROUPS][2 * EMD_R]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp % EMD_RGROUPS, ch = warp / EMD_RGROUPS;
   const float* rows = p.rows + (size_t)b * p.nr * 3;
   const float* cols = p.cols + (size_t)b * p.nc * 3;
   auto ldv = [](const float* q) -> float { return COHERENT ? __ldcg(q) : *q; };
+  const unsigned long long lvlA2 = f2_pack(p.lvlA, p.lvlA), lvlB2 = f2_pack(p.lvlB, p.lvlB), l2e2 = f2_pack(LOG2E, LOG2E);
   for (int base = row_begin; base < row_end; base += EMD_ROWS_PER_CTA) {
-    const int r0 = base + warp * EMD_R;
-    float rx[EMD_R], ry[EMD_R], rz[EMD_R], sa[EMD_R], sb[EMD_R];
+    const int r0 = base + rg * EMD_R;
+    unsigned long long nrx[2], nry[2], nrz[2], sa[2], sb[2];
 #pragma unroll
-    for (int i = 0; i < EMD_R; ++i) {
-      const int r = min(r0 + i, p.nr - 1);
-      rx[i] = rows[r * 3]; ry[i] = rows[r * 3 + 1]; rz[i] = rows[r * 3 + 2];
-      sa[i] = 0.f; sb[i] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int ra = min(r0 + 2 * h, p.nr - 1), rb = min(r0 + 2 * h + 1, p.nr - 1);
+      nrx[h] = f2_pack(-rows[ra * 3], -rows[rb * 3]);
+      nry[h] = f2_pack(-rows[ra * 3 + 1], -rows[rb * 3 + 1]);
+      nrz[h] = f2_pack(-rows[ra * 3 + 2], -rows[rb * 3 + 2]);
+      sa[h] = 0ull; sb[h] = 0ull;
     }
     for (int c0 = 0; c0 < p.nc; c0 += EMD_CHUNK) {
       const int cn = min(EMD_CHUNK, p.nc - c0);
@@ -110,30 +120,51 @@ __device__ __forceinline__ void emd_sweep_rows(const EmdSweepParams& p, int b, i
       }
       __syncthreads();
       if (r0 < row_end) {
-        for (int c = lane; c < cn; c += 32) {
+        for (int c = ch * 32 + lane; c < cn; c += 32 * EMD_CSPLIT) {
           const float4 q = s_col[c];
-          const float vb = FUSED ? s_vb[c] : 0.f;
+          const unsigned long long qx = f2_pack(q.x, q.x), qy = f2_pack(q.y, q.y), qz = f2_pack(q.z, q.z);
+          const unsigned long long qw = f2_pack(q.w, q.w);
+          unsigned long long vb2 = 0ull;
+          if (FUSED) { const float vb = s_vb[c]; vb2 = f2_pack(vb, vb); }
 #pragma unroll
-          for (int i = 0; i < EMD_R; ++i) {
-            const float d2 = emd_d2(rx[i], ry[i], rz[i], q.x, q.y, q.z);
-            sa[i] = fmaf(emd_exp(p.lvlA, d2), q.w, sa[i]);
-            if (FUSED) sb[i] = fmaf(emd_exp(p.lvlB, d2), vb, sb[i]);
+          for (int h = 0; h < 2; ++h) {
+            // d2 = fma(dz, dz, fma(dx, dx, dy*dy)), d = column - row   (emd_d2, per lane)
+            const unsigned long long dx = f2_add(qx, nrx[h]), dy = f2_add(qy, nry[h]), dz = f2_add(qz, nrz[h]);
+            const unsigned long long d2 = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+            float t0, t1;
+            f2_unpack(f2_mul(f2_mul(lvlA2, d2), l2e2), t0, t1);              // emd_exp: (level*d2)*log2e, then ex2
+            sa[h] = f2_fma(f2_pack(ex2_approx(t0), ex2_approx(t1)), qw, sa[h]);
+            if (FUSED) {
+              f2_unpack(f2_mul(f2_mul(lvlB2, d2), l2e2), t0, t1);
+              sb[h] = f2_fma(f2_pack(ex2_approx(t0), ex2_approx(t1)), vb2, sb[h]);
+            }
           }
         }
       }
     }
+    float fa[EMD_R], fb[EMD_R];
+    f2_unpack(sa[0], fa[0], fa[1]); f2_unpack(sa[1], fa[2], fa[3]);
+    f2_unpack(sb[0], fb[0], fb[1]); f2_unpack(sb[1], fb[2], fb[3]);
 #pragma unroll
     for (int i = 0; i < EMD_R; ++i) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        sa[i] += __shfl_xor_sync(L3D_FULL_MASK, sa[i], o);
-        if (FUSED) sb[i] += __shfl_xor_sync(L3D_FULL_MASK, sb[i], o);
+        fa[i] += __shfl_xor_sync(L3D_FULL_MASK, fa[i], o);
+        if (FUSED) fb[i] += __shfl_xor_sync(L3D_FULL_MASK, fb[i], o);
       }
     }
     if (lane < EMD_R) {
-      float S = sa[0], S2 = sb[0];
+      float S = fa[0], S2 = fb[0];
 #pragma unroll
-      for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = sa[i]; S2 = sb[i]; }
+      for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = fa[i]; S2 = fb[i]; }
+      s_part[ch][rg][lane] = S;
+      s_part[ch][rg][EMD_R + lane] = S2;
+    }
+    __syncthreads();
+    if (ch == 0 && lane < EMD_R) {
+      float S = s_part[0][rg][lane], S2 = s_part[0][rg][EMD_R + lane];
+#pragma unroll
+      for (int k = 1; k < EMD_CSPLIT; ++k) { S += s_part[k][rg][lane]; S2 += s_part[k][rg][EMD_R + lane]; }
       const int r = r0 + lane;
       if (r < row_end && r < p.nr) {
         const size_t o = (size_t)b * p.nr + r;
@@ -142,7 +173,7 @@ __device__ __forceinline__ void emd_sweep_rows(const EmdSweepParams& p, int b, i
           if (p.init) p.remain[o] = rem;
           p.ratio_out[o] = rem / (1e-9f + S);                       // emd.cuh:40,60
         } else if (p.phase == EMD_PH2) {
-          const float rem = p.init ? p.multi : ldv(p.remain + o);   // init: remainR = multiR (emd.cuh:24-25)
+          const float rem = ldv(p.remain + o);
           const float sumr = S * rem;                                 // emd.cuh:110
           const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
           p.ratio_out[o] = consumption * rem;
@@ -163,8 +194,9 @@ template <bool FUSED>
 __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(const EmdSweepParams p) {
   __shared__ float4 s_col[EMD_CHUNK];
   __shared__ float s_vb[FUSED ? EMD_CHUNK : 1];
+  __shared__ float s_part[EMD_CSPLIT][EMD_RGROUPS][2 * EMD_R];
   const int r0 = blockIdx.x * EMD_ROWS_PER_CTA;
-  emd_sweep_rows<FUSED, false>(p, blockIdx.y, r0, min(r0 + EMD_ROWS_PER_CTA, p.nr), s_col, s_vb);
+  emd_sweep_rows<FUSED, false>(p, blockIdx.y, r0, min(r0 + EMD_ROWS_PER_CTA, p.nr), s_col, s_vb, s_part);
 }
 
 // ---- persistent forward: all 20 sweeps in ONE launch --------------------------------------------------------
@@ -208,6 +240,7 @@ __device__ __forceinline__ bool emd_item_barrier(unsigned int* ctr, unsigned int
 __global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPersistParams q) {
   __shared__ float4 s_col[EMD_CHUNK];
   __shared__ float s_vb[EMD_CHUNK];
+  __shared__ float s_part[EMD_CSPLIT][EMD_RGROUPS][2 * EMD_R];
   __shared__ int s_flag;
   const int C = q.ctas_per_item;
   const int b = blockIdx.x / C, cx = blockIdx.x - b * C;
@@ -229,7 +262,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPe
     EmdSweepParams p{};
     p.rows = q.xyz1; p.cols = q.xyz2; p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH1;
     p.lvlA = q.lvl[0]; p.vA = q.remainR; p.remain = q.remainL; p.ratio_out = q.ratioL; p.multi = q.multiL; p.init = 1;
-    emd_sweep_rows<false, true>(p, b, l0, l1, s_col, s_vb);
+    emd_sweep_rows<false, true>(p, b, l0, l1, s_col, s_vb, s_part);
   }
   if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
   for (int it = 0; it < EMD_LEVELS; ++it) {
@@ -237,7 +270,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPe
       EmdSweepParams p{};
       p.rows = q.xyz2; p.cols = q.xyz1; p.B = q.B; p.nr = q.m; p.nc = q.n; p.phase = EMD_PH2;
       p.lvlA = q.lvl[it]; p.vA = q.ratioL + (size_t)it * Bn; p.remain = q.remainR; p.ratio_out = q.ratioR + (size_t)it * Bm;
-      emd_sweep_rows<false, true>(p, b, r0, r1, s_col, s_vb);
+      emd_sweep_rows<false, true>(p, b, r0, r1, s_col, s_vb, s_part);
     }
     if (it + 1 == EMD_LEVELS) break;
     if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
@@ -246,7 +279,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPe
       p.rows = q.xyz1; p.cols = q.xyz2; p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH3_PH1;
       p.lvlA = q.lvl[it]; p.vA = q.ratioR + (size_t)it * Bm; p.lvlB = q.lvl[it + 1]; p.vB = q.remainR;
       p.remain = q.remainL; p.ratio_in = q.ratioL + (size_t)it * Bn; p.ratio_out = q.ratioL + (size_t)(it + 1) * Bn;
-      emd_sweep_rows<true, true>(p, b, l0, l1, s_col, s_vb);
+      emd_sweep_rows<true, true>(p, b, l0, l1, s_col, s_vb, s_part);
     }
     if (!emd_item_barrier(ctr, ++phase * C, q.err, &s_flag)) return;
   }
@@ -268,31 +301,75 @@ struct EmdFinalParams {
   float lvl[EMD_LEVELS];
 };
 
+constexpr int EMD_FK = 1024;                                  // k-tile of the final pass
+constexpr size_t EMD_FINAL_SMEM = (size_t)(EMD_LEVELS + 4) * EMD_FK * sizeof(float);
 __global__ void __launch_bounds__(EMD_THREADS) emd_final_kernel(const EmdFinalParams p) {
+  // the 10 ratioL rows of the current k-tile and the (negated) row cloud are staged once per CTA and shared by its
+  // 8 match rows; a lane handles the pair (k, k + 32) with packed f32x2 arithmetic
+  extern __shared__ __align__(16) float fsm[];
+  float(*s_rl)[EMD_FK] = reinterpret_cast<float(*)[EMD_FK]>(fsm);
+  float4* s_nx1 = reinterpret_cast<float4*>(fsm + EMD_LEVELS * EMD_FK);
   __shared__ float red[EMD_WARPS];
   __shared__ bool is_last;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l = blockIdx.x * EMD_WARPS + warp;
   const float* x1 = p.xyz1 + (size_t)b * p.n * 3;
+  const unsigned long long l2e2 = f2_pack(LOG2E, LOG2E);
   float acc = 0.f;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  float rr[EMD_LEVELS];
+#pragma unroll
+  for (int j = 0; j < EMD_LEVELS; ++j) rr[j] = 0.f;
   if (l < p.m) {
     const float* q = p.xyz2 + ((size_t)b * p.m + l) * 3;
-    const float qx = q[0], qy = q[1], qz = q[2];
-    float rr[EMD_LEVELS];
+    qx = q[0]; qy = q[1]; qz = q[2];
 #pragma unroll
     for (int j = 0; j < EMD_LEVELS; ++j) rr[j] = p.ratioR[((size_t)j * p.B + b) * p.m + l];
-    for (int k = lane; k < p.n; k += 32) {
-      const float d2 = emd_d2(x1[k * 3], x1[k * 3 + 1], x1[k * 3 + 2], qx, qy, qz);
-      float mt = 0.f;
+  }
+  const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
+  for (int k0 = 0; k0 < p.n; k0 += EMD_FK) {
+    const int kn = min(EMD_FK, p.n - k0);
+    __syncthreads();
+    for (int i = tid; i < kn; i += EMD_THREADS) {
+      const float* a = x1 + (size_t)(k0 + i) * 3;
+      s_nx1[i] = make_float4(-a[0], -a[1], -a[2], 0.f);
 #pragma unroll
-      for (int j = 0; j < EMD_LEVELS; ++j) {
-        const float e = (j == EMD_LEVELS - 1) ? 1.0f : emd_exp(p.lvl[j], d2);
-        const float rl = p.ratioL[((size_t)j * p.B + b) * p.n + k];
-        mt += e * rl * rr[j];                                       // match += w   (emd.cuh:157-158)
+      for (int j = 0; j < EMD_LEVELS; ++j) s_rl[j][i] = p.ratioL[((size_t)j * p.B + b) * p.n + k0 + i];
+    }
+    __syncthreads();
+    if (l < p.m) {
+      for (int kk = lane; kk < kn; kk += 64) {
+        const bool v1 = kk + 32 < kn;
+        const int k1 = v1 ? kk + 32 : kk;
+        const float4 a0 = s_nx1[kk], a1 = s_nx1[k1];
+        const unsigned long long dx = f2_add(qx2, f2_pack(a0.x, a1.x)), dy = f2_add(qy2, f2_pack(a0.y, a1.y)),
+                                 dz = f2_add(qz2, f2_pack(a0.z, a1.z));
+        const unsigned long long d2 = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+        unsigned long long mt = 0ull;
+#pragma unroll
+        for (int j = 0; j < EMD_LEVELS; ++j) {
+          const unsigned long long rl = f2_pack(s_rl[j][kk], s_rl[j][k1]);
+          const unsigned long long rj = f2_pack(rr[j], rr[j]);
+          if (j == EMD_LEVELS - 1) {
+            mt = f2_add(mt, f2_mul(rl, rj));                                // level 0: exp(0) = 1
+          } else {
+            float t0, t1;
+            f2_unpack(f2_mul(f2_mul(f2_pack(p.lvl[j], p.lvl[j]), d2), l2e2), t0, t1);
+            mt = f2_add(mt, f2_mul(f2_mul(f2_pack(ex2_approx(t0), ex2_approx(t1)), rl), rj));   // match += w (emd.cuh:157-158)
+          }
+        }
+        float m0, m1, e0, e1;
+        f2_unpack(mt, m0, m1);
+        f2_unpack(d2, e0, e1);
+        float* mrow = p.match ? p.match + (size_t)b * p.n * p.m + (size_t)l * p.n + k0 : nullptr;
+        if (mrow) mrow[kk] = m0;
+        acc = fmaf(sqrtf(e0), m0, acc);                                     // emd.cuh:225-226
+        if (v1) {
+          if (mrow) mrow[kk + 32] = m1;
+          acc = fmaf(sqrtf(e1), m1, acc);
+        }
       }
-      if (p.match) p.match[(size_t)b * p.n * p.m + (size_t)l * p.n + k] = mt;
-      acc = fmaf(sqrtf(d2), mt, acc);                               // emd.cuh:225-226
     }
   }
 #pragma unroll
@@ -461,7 +538,7 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, emd_persistent_kernel, EMD_THREADS, 0) != cudaSuccess) occ = 0;
-      if (occ > 2) occ = 2;                 // 16 warps/SM already cover the MUFU latency; fewer CTAs = cheaper barriers
+      if (occ > 4) occ = 4;                 // 32 warps/SM: while one item's CTAs sit in a barrier the others sweep
       c_cap = coop ? sms * occ : 0;
       c_dev = dev;
     }
@@ -534,7 +611,16 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
   fp.xyz1 = xyz1_dev; fp.xyz2 = xyz2_dev; fp.ratioL = ratioL; fp.ratioR = ratioR;
   fp.match = match_dev; fp.partial = partial; fp.cost = cost_dev; fp.ticket = ticket;
   fp.B = B; fp.n = n; fp.m = m;
-  emd_final_kernel<<<dim3(gx_final, B), EMD_THREADS, 0, s>>>(fp);
+  {
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64)
+      std::call_once(once[dev], [] { cudaFuncSetAttribute(emd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMD_FINAL_SMEM); });
+    else
+      cudaFuncSetAttribute(emd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMD_FINAL_SMEM);
+  }
+  emd_final_kernel<<<dim3(gx_final, B), EMD_THREADS, EMD_FINAL_SMEM, s>>>(fp);
   count_launch();
   L3D_LAUNCH_CHECK();
   return L3D_OK;

@@ -119,31 +119,12 @@ __device__ __forceinline__ float4 knn_pack(float x, float y, float z) {
   return make_float4(x, y, z, w);
 }
 
-// ---- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): two independent IEEE fp32 lanes per instruction, each
-// rounded exactly like the scalar op, so a key computed in a packed lane is bit-identical to knn_key<>.
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+#ifndef L3D_KNN_TWO_PASS
+#define L3D_KNN_TWO_PASS 0   // packed path: recompute the keys for the mask instead of holding 32 per row in registers
+#endif
+#ifndef L3D_KNN_TP_UNROLL
+#define L3D_KNN_TP_UNROLL 4  // two-pass path: candidate pairs in flight per loop trip (bounds the live LDS results)
+#endif
 #ifndef L3D_KNN_F32X2
 #define L3D_KNN_F32X2 1      // expansion-mode k <= 24 path: evaluate two candidates per FFMA2 (pair layout below)
 #endif
@@ -448,6 +429,74 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
     // re-evaluated with the full formula below), so the selection stays exact as long as the s-space
     // threshold is lowered to cover every s that can round to the k-th key (thr computation below).
     constexpr bool DEFER = (L3D_KNN_DEFER_QW != 0) && MODE == MODE_EXPANSION_NEG;
+    constexpr bool TWO_PASS = PAIRS && (L3D_KNN_TWO_PASS != 0);
+    constexpr int TPU = L3D_KNN_TP_UNROLL;
+    uint32_t mask[R];
+    int cnt[R], incl[R], total[R];
+    // the s-space threshold of a row from its sorted lane maxima (mx: lane l holds the l-th largest maximum)
+    auto row_threshold = [&](int r, float mxr) -> float {
+      float thr = __shfl_sync(L3D_FULL_MASK, mxr, k - 1);
+      if (DEFER) {
+        // kb: the exact key every survivor must reach (k-th lane maximum in key space, or the running
+        // k-th best).  K(s) >= kb implies s >= kb + |q|^2 - ulp(kb)/2, so rounding that bound DOWN
+        // (twice, with |kb| 2^-23 >= ulp/2 as the margin) keeps every such s; it admits at most the
+        // few s within ~2 ulp below, which the exact re-evaluation sorts out.
+        const float kb = fmaxf(__fsub_rn(thr, q[r].w), kth[r]);
+        thr = __fadd_rd(__fadd_rd(kb, q[r].w), -__fmul_rn(fmaxf(fabsf(kb), 1e-30f), 1.1920929e-7f));
+      } else {
+        thr = fmaxf(thr, kth[r]);
+      }
+      return thr;
+    };
+    if constexpr (TWO_PASS) {
+      // The 32 keys of a lane are never held in registers: pass 1 keeps only the running lane maximum, pass 2
+      // re-evaluates the same packed expressions (same bits) and turns each key straight into its mask bit.
+      // ~64 registers less per thread (more resident warps) for 64 more FFMA2 per row.
+      const ulonglong2* pxy = pair_xy + t * (KNN_TILE / 2) + lane;
+      const ulonglong2* pzw = pair_zw + t * (KNN_TILE / 2) + lane;
+      unsigned long long qx2[R], qy2[R], qz2[R];
+      float m[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        qx2[r] = f2_pack(q[r].x, q[r].x); qy2[r] = f2_pack(q[r].y, q[r].y); qz2[r] = f2_pack(q[r].z, q[r].z);
+        m[r] = -INFINITY;
+      }
+      const unsigned long long two2 = f2_pack(2.0f, 2.0f);
+#pragma unroll TPU
+      for (int pe = 0; pe < 16; ++pe) {
+        const ulonglong2 a = pxy[pe * 32], bz = pzw[pe * 32];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long dot = f2_fma(qz2[r], bz.x, f2_fma(qy2[r], a.y, f2_mul(qx2[r], a.x)));
+          float s0, s1;
+          f2_unpack(f2_fma(two2, dot, bz.y), s0, s1);
+          m[r] = fmaxf(m[r], fmaxf(s0, s1));
+        }
+      }
+      warp_sort32_keys_desc_x<R>(m, lane);
+      unsigned long long nthr[R];
+      uint32_t neg[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float thr = row_threshold(r, m[r]);
+        nthr[r] = f2_pack(-thr, -thr);
+        neg[r] = 0u;
+      }
+#pragma unroll TPU
+      for (int pe = 15; pe >= 0; --pe) {
+        const ulonglong2 a = pxy[pe * 32], bz = pzw[pe * 32];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long dot = f2_fma(qz2[r], bz.x, f2_fma(qy2[r], a.y, f2_mul(qx2[r], a.x)));
+          float s0, s1;
+          f2_unpack(f2_add(f2_fma(two2, dot, bz.y), nthr[r]), s0, s1);
+          neg[r] = __funnelshift_l(__float_as_uint(s1), neg[r], 1);
+          neg[r] = __funnelshift_l(__float_as_uint(s0), neg[r], 1);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) { mask[r] = ~neg[r]; cnt[r] = __popc(mask[r]); }
+    } else {
     float d[R][32];
     if constexpr (PAIRS) {
       // two candidates per instruction: s = fma(2, fma(qz,cz, fma(qy,cy, qx*cx)), -|c|^2), same op order per lane
@@ -484,23 +533,12 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
       float m = d[r][0];
 #pragma unroll
       for (int e = 1; e < 32; ++e) m = fmaxf(m, d[r][e]);
-      mx[r] = warp_sort32_keys_desc(m, lane);
+      mx[r] = m;
     }
-    uint32_t mask[R];
-    int cnt[R], incl[R], total[R];
+    warp_sort32_keys_desc_x<R>(mx, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float thr = __shfl_sync(L3D_FULL_MASK, mx[r], k - 1);
-      if (DEFER) {
-        // kb: the exact key every survivor must reach (k-th lane maximum in key space, or the running
-        // k-th best).  K(s) >= kb implies s >= kb + |q|^2 - ulp(kb)/2, so rounding that bound DOWN
-        // (twice, with |kb| 2^-23 >= ulp/2 as the margin) keeps every such s; it admits at most the
-        // few s within ~2 ulp below, which the exact re-evaluation sorts out.
-        const float kb = fmaxf(__fsub_rn(thr, q[r].w), kth[r]);
-        thr = __fadd_rd(__fadd_rd(kb, q[r].w), -__fmul_rn(fmaxf(fabsf(kb), 1e-30f), 1.1920929e-7f));
-      } else {
-        thr = fmaxf(thr, kth[r]);
-      }
+      const float thr = row_threshold(r, mx[r]);
       // survivor mask: bit e = (d[e] >= thr).  d - thr is +0 on equality, so the survivors are the
       // differences with a clear sign bit; one FADD (FMA pipe) + one funnel shift (ALU pipe) per key
       // instead of FSETP + predicated OR (two ALU-pipe instructions; the ALU pipe is the busier one).
@@ -522,6 +560,7 @@ __device__ __forceinline__ void knn_rows_v2(const KnnParams& p, const float4* __
       const uint32_t mk = ~neg;
       mask[r] = mk;
       cnt[r] = __popc(mk);
+    }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) incl[r] = warp_inclusive_scan(cnt[r], lane);

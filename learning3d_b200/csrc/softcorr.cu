@@ -77,6 +77,10 @@ struct SoftCorrParams {
   // EPI_SQDIST (feature-space square_distance / RPMNet affinity): optional per-item affinity transform
   const float* aff_beta;  // [B] or null: out = -beta[b] * (dist - alpha[b])     (rpmnet.py:266-272)
   const float* aff_alpha; // [B]
+  // EPI_STATS / EPI_PROBS_T (attention, utils/transformer.py:17-23): row statistics of softmax(a^T b / sqrt(D)) and
+  // the TRANSPOSED probabilities P^T [B, Nt, Ns] (the B operand of the P.V GEMM, l3d_conv1x1_bn_relu_maxk)
+  float* stats;           // [B, Ns, 2]: (running max in log2 units, sum of 2^(s - max))
+  float* probs_t;         // [B, Nt, Ns]
   int kmajor;             // generic pipeline only: operands are [B, N, D] (channels contiguous) instead of [B, D, N]
   int* err;               // device error word (0 = ok)
   float* part;            // split target range only: partial softmax states [B, Ns, gridDim.z, 8]
@@ -159,6 +163,8 @@ __device__ __forceinline__ float sc_matrix_value(float v, float xa_i, float xb_j
   // pd = ((-|b_j|^2) + 2 a_i.b_j) - |a_i|^2  (model_common_utils.py:5-7, same association as knn.cu)
   return __fsub_rn(fmaf(2.0f, v, -xb_j), xa_i);
 }
+constexpr int EPI_STATS = 3;         // attention pass 1: online (max, sum) of the scaled score rows -> stats [B,Ns,2]
+constexpr int EPI_PROBS_T = 4;       // attention pass 2: softmax probabilities, transposed -> probs_t [B,Nt,Ns]
 constexpr int EPI_SOFTMAX_XYZ = 0;   // SVD head: online softmax, xyz-weighted sums  -> out [B,3,Ns]
 constexpr int EPI_KEYS = 1;          // feature-space kNN: negated expansion distances -> keys [B,Ns,Nt]
 
@@ -229,6 +235,12 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
     float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     constexpr bool MATRIX = (EPI == EPI_KEYS || EPI == EPI_SQDIST);
     const float xi = (MATRIX && i < p.Ns) ? __ldg(p.xx_a + (size_t)b * p.Ns + i) : 0.f;
+    // EPI_PROBS_T: this row's softmax statistics from the EPI_STATS pass
+    float pm = 0.f, pinv = 0.f;
+    if (EPI == EPI_PROBS_T && i < p.Ns) {
+      pm = __ldg(p.stats + ((size_t)b * p.Ns + i) * 2);
+      pinv = __fdividef(1.f, __ldg(p.stats + ((size_t)b * p.Ns + i) * 2 + 1));
+    }
     const bool aff = (EPI == EPI_SQDIST) && p.aff_beta != nullptr;
     const float a_beta = aff ? __ldg(p.aff_beta + b) : 0.f, a_alpha = aff ? __ldg(p.aff_alpha + b) : 0.f;
     bool ok = true;
@@ -236,7 +248,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       const int a = jb & 1;
       const int j0 = (jb0 + jb) * SC_BN;
 #pragma unroll
-      for (int jj = tid; jj < SC_BN; jj += SC_EPI_THREADS) {
+      for (int jj = tid; jj < ((EPI == EPI_STATS || EPI == EPI_PROBS_T) ? 0 : SC_BN); jj += SC_EPI_THREADS) {
         const int j = j0 + jj;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < p.Nt) {
@@ -249,7 +261,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         }
         sh->xyz[a][jj] = q;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (EPI != EPI_STATS && EPI != EPI_PROBS_T) asm volatile("bar.sync 1, 128;" ::: "memory");
       if (!mbar_wait_bounded(&sh->acc_full[a], (uint32_t)((jb >> 1) & 1))) { ok = false; break; }
       __syncwarp();
       tc_fence_after();
@@ -299,6 +311,17 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
           }
           continue;
         }
+        if (EPI == EPI_PROBS_T) {
+          // P[i, j] = 2^(s c - m_i) / l_i, stored TRANSPOSED: for a fixed column j the 32 lanes (rows i) write one
+          // 128-byte line of probs_t[b, j, :]
+          if (i < p.Ns) {
+            float* dst = p.probs_t + ((size_t)b * p.Nt + j0 + ch * 32) * p.Ns + i;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (ch * 32 + e < nvalid) dst[(size_t)e * p.Ns] = __fmul_rn(ex2_approx(fmaf(v[e], c, -pm)), pinv);
+          }
+          continue;
+        }
         if (nvalid - ch * 32 < 32) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -315,9 +338,11 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const float pe = ex2_approx(fmaf(v[e], c, -m));
-          const float4 q = xz[e];
           l = __fadd_rn(l, pe);
-          ax = fmaf(pe, q.x, ax); ay = fmaf(pe, q.y, ay); az = fmaf(pe, q.z, az);
+          if (EPI != EPI_STATS) {
+            const float4 q = xz[e];
+            ax = fmaf(pe, q.x, ax); ay = fmaf(pe, q.y, ay); az = fmaf(pe, q.z, az);
+          }
         }
       }
       tc_fence_before();
@@ -345,6 +370,14 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         float* dst = p.keys + ((size_t)b * p.Ns + i) * p.Nt;
         for (int j = 0; j < p.Nt; ++j) dst[j] = qnan;
       }
+    }
+    if (EPI == EPI_STATS && i < p.Ns) {
+      const float qn = __int_as_float(0x7fc00000);
+      p.stats[((size_t)b * p.Ns + i) * 2] = ok ? m : qn;
+      p.stats[((size_t)b * p.Ns + i) * 2 + 1] = ok ? l : qn;
+    }
+    if (EPI == EPI_PROBS_T && !ok && i < p.Ns) {
+      for (int j = 0; j < p.Nt; ++j) p.probs_t[((size_t)b * p.Nt + j) * p.Ns + i] = __int_as_float(0x7fc00000);
     }
     if (EPI == EPI_SOFTMAX_XYZ && ok && i < p.Ns && p.part) {
       // split target range: leave (running max in log2 units, sum, sum*xyz) for the merge kernel
@@ -592,7 +625,7 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   }
   const long slots = pair ? sm_count / 2 : sm_count;   // 1 CTA per SM; a pair needs both SMs of a TPC
   int jsplit = 1;
-  if (g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
+  if (EPI != EPI_STATS && g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
     jsplit = (int)((slots + units - 1) / units);
     if (g_softcorr_split > 0) jsplit = g_softcorr_split;
     if (jsplit > tiles) jsplit = tiles;
@@ -769,6 +802,33 @@ extern "C" int l3d_knn_features(const float* x_dev, int B, int C, int N, int k, 
   int rc = sc_launch<EPI_KEYS>(p, stream);
   if (rc != L3D_OK) return rc;
   return knn_select_from_matrix(keys, rows, N, k, reinterpret_cast<long long*>(idx_dev), (cudaStream_t)stream);
+}
+
+// ---- attention (utils/transformer.py:17-23): softmax(q k^T / sqrt(d_k)) in two passes over the tcgen05 score
+// pipeline; the probabilities leave the kernel transposed, ready to be the activation operand of the P.V GEMM.
+// q_dev [BH, D, Nq], k_dev [BH, D, Nk] (channel-major per batch x head) -> stats_dev [BH, Nq, 2]
+extern "C" int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk,
+                                   float* stats_dev, void* stream) {
+  if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
+  if (BH == 0 || Nq == 0) return L3D_OK;
+  if (!q_dev || !k_dev || !stats_dev) return L3D_ERR_INVALID;
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = stats_dev;
+  p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
+  return sc_launch<EPI_STATS>(p, stream);
+}
+// ... + stats_dev -> probs_t_dev [BH, Nk, Nq] = softmax(q^T k / sqrt(D), over k) transposed
+extern "C" int l3d_attention_probs_t(const float* q_dev, const float* k_dev, const float* stats_dev, int BH, int D,
+                                     int Nq, int Nk, float* probs_t_dev, void* stream) {
+  if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
+  if (BH == 0 || Nq == 0) return L3D_OK;
+  if (!q_dev || !k_dev || !stats_dev || !probs_t_dev) return L3D_ERR_INVALID;
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = const_cast<float*>(stats_dev); p.probs_t = probs_t_dev;
+  p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
+  return sc_launch<EPI_PROBS_T>(p, stream);
 }
 
 extern "C" int l3d_soft_correspondence(const float* src_emb, const float* tgt_emb, const float* tgt_xyz,

@@ -2,10 +2,10 @@
 names of learning3d/utils/transformer.py:219-243 so reference checkpoints load
 (`model.encoder.layers.0.self_attn.linears.0.weight`, `...sublayer.0.norm.a_2`, ...).
 
-Dense contraction, not a neighbour-search op: it is a CALLER kept for API compatibility (SURVEY.md §8f
-rank 2).  The one B200-minded change is that attention goes through torch's fused
-scaled_dot_product_attention, so the [B, heads, N, N] score tensor of the reference
-(transformer.py:17-23) is never materialised.
+SURVEY.md §8f rank 2.  In eval mode / no-grad the whole forward runs on the tcgen05 pipelines with channel-major
+activations (utils/transformer_fused.py: linear layers, attention scores + p.v, LayerNorm).  Under autograd the
+torch layers below run; there attention goes through torch's fused scaled_dot_product_attention, so the
+[B, heads, N, N] score tensor of the reference (transformer.py:17-23) is not materialised either.
 """
 import copy
 import math
@@ -137,9 +137,14 @@ class Transformer(nn.Module):
         self.model = _EncoderDecoder(_Encoder(_EncoderLayer(emb_dims, n_heads, ff_dims), n_blocks),
                                      _Decoder(_DecoderLayer(emb_dims, n_heads, ff_dims), n_blocks))
 
-    def forward(self, *input):
+    def _l3d_torch_forward(self, *input):
+        """The reference's data flow (transformer.py:255-263) in torch ops: training / autograd path."""
         src = input[0].transpose(2, 1).contiguous()
         tgt = input[1].transpose(2, 1).contiguous()
         tgt_embedding = self.model(src, tgt).transpose(2, 1).contiguous()
         src_embedding = self.model(tgt, src).transpose(2, 1).contiguous()
         return src_embedding, tgt_embedding
+
+    def forward(self, *input):
+        from .transformer_fused import transformer_forward
+        return transformer_forward(self, *input)

@@ -1,5 +1,5 @@
 import os, sys, subprocess, glob
-ROOT='/root/repo'
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE=r'''
 import sys, numpy as np, torch
 sys.path.insert(0, %r)

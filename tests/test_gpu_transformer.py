@@ -1,0 +1,97 @@
+"""DCP's transformer on the tcgen05 pipelines (utils/transformer_fused.py): channel-major linear layers, attention in
+two score passes + the p.v GEMM, LayerNorm.  Floating-point kernels: checked against fp64 evaluations of the
+reference's expressions (utils/transformer.py:17-23,128-137,175-194) with the fp32-GEMM error model, and the whole
+forward against the module's own torch path (TF32 disabled)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_linear_cm_bias_relu_residual():
+    from learning3d_b200.utils.transformer_fused import linear_cm
+    torch.manual_seed(0)
+    for (B, K, M, N) in [(3, 512, 512, 1024), (2, 512, 1024, 260), (1, 1024, 512, 64), (2, 72, 200, 132)]:
+        lin = torch.nn.Linear(K, M).to(DEV)
+        x = torch.randn(B, K, N, device=DEV)
+        res = torch.randn(B, M, N, device=DEV)
+        for relu, r in ((False, None), (True, None), (False, res)):
+            got = linear_cm(x, lin, relu=relu, residual=r).double()
+            y = torch.einsum("mk,bkn->bmn", lin.weight.double(), x.double()) + lin.bias.double()[None, :, None]
+            mag = torch.einsum("mk,bkn->bmn", lin.weight.double().abs(), x.double().abs()) + 1.0
+            if relu:
+                y = y.clamp_min(0)
+            if r is not None:
+                y = y + r.double()
+            err = ((got - y).abs() / mag).max().item()
+            assert err < 4e-6, (B, K, M, N, relu, err)
+
+
+def test_layernorm_cm():
+    from learning3d_b200.utils.transformer import _Norm
+    from learning3d_b200.utils.transformer_fused import layernorm_cm
+    torch.manual_seed(1)
+    for (B, D, N) in [(2, 512, 1024), (3, 96, 77), (1, 8, 5)]:
+        norm = _Norm(D).to(DEV)
+        with torch.no_grad():
+            norm.a_2.uniform_(0.5, 1.5); norm.b_2.normal_(0, 0.2)
+        x = torch.randn(B, D, N, device=DEV) * 3 + 1
+        got = layernorm_cm(x, norm)
+        xd = x.double().transpose(1, 2)
+        want = (norm.a_2.double() * (xd - xd.mean(-1, keepdim=True)) / (xd.std(-1, keepdim=True) + norm.eps)
+                + norm.b_2.double()).transpose(1, 2)
+        assert (got.double() - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,h,Nq,Nk", [(2, 4, 256, 256), (1, 4, 132, 520), (3, 2, 1024, 1024)])
+def test_attention_cm_vs_fp64(B, h, Nq, Nk):
+    from learning3d_b200.utils.transformer import MultiHeadedAttention
+    from learning3d_b200.utils.transformer_fused import attention_cm
+    torch.manual_seed(B + Nq)
+    d = h * 128
+    attn = MultiHeadedAttention(h, d).to(DEV).eval()
+    xq = torch.randn(B, d, Nq, device=DEV)
+    xkv = torch.randn(B, d, Nk, device=DEV) * 1.5
+    res = torch.randn(B, d, Nq, device=DEV)
+    with torch.no_grad():
+        got = attention_cm(attn, xq, xkv, res).double()
+        L = [(l.weight.double(), l.bias.double()) for l in attn.linears]
+        q = (xq.double().transpose(1, 2) @ L[0][0].t() + L[0][1]).view(B, Nq, h, 128).transpose(1, 2)
+        k = (xkv.double().transpose(1, 2) @ L[1][0].t() + L[1][1]).view(B, Nk, h, 128).transpose(1, 2)
+        v = (xkv.double().transpose(1, 2) @ L[2][0].t() + L[2][1]).view(B, Nk, h, 128).transpose(1, 2)
+        p = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(128), dim=-1)
+        ctx = (p @ v).transpose(1, 2).reshape(B, Nq, d)
+        want = (ctx @ L[3][0].t() + L[3][1]).transpose(1, 2) + res.double()
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    print("attention B=%d h=%d Nq=%d Nk=%d: max |err| = %.3g (|out| max %.3g)" % (B, h, Nq, Nk, err, scale))
+    assert err < 2e-5 * max(1.0, scale)
+
+
+def test_transformer_forward_fused_vs_torch_path():
+    from learning3d_b200.utils.transformer import Transformer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    net = Transformer(512, 1, 0.0, 1024, 4).to(DEV).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if hasattr(m, "a_2"):
+                m.a_2.uniform_(0.8, 1.2); m.b_2.normal_(0, 0.1)
+    src = torch.randn(4, 512, 1024, device=DEV)
+    tgt = torch.randn(4, 512, 1024, device=DEV)
+    with torch.no_grad():
+        a, b = net(src, tgt)
+        wa, wb = net._l3d_torch_forward(src, tgt)
+    for got, want, name in ((a, wa, "src_embedding"), (b, wb, "tgt_embedding")):
+        err = (got - want).abs().max().item()
+        print("transformer %s: max |fused - torch| = %.3g (|x| max %.3g)" % (name, err, want.abs().max().item()))
+        assert err < 3e-5 * max(1.0, want.abs().max().item())
+    # autograd keeps working (torch path)
+    src.requires_grad_(True)
+    a, b = net(src, tgt)
+    (a.mean() + b.mean()).backward()
+    assert src.grad is not None
