@@ -166,8 +166,17 @@ class FlowNet3D(nn.Module):
         return lvl1, self.sa2(*lvl1)
 
     def forward(self, pc1, pc2, feature1, feature2):
-        (p1, f1), (p2, f2) = self._encode(pc1, feature1)            # frame 1 pyramid
-        _, (q2, g2) = self._encode(pc2, feature2)                    # frame 2, coarse level only
+        if not self.training and pc1.shape == pc2.shape and feature1.shape == feature2.shape:
+            # eval: both frames go through the shared encoder as ONE batch of 2B clouds (BatchNorm uses running
+            # statistics, so the result equals the two separate passes of models/flownet3d.py:311-314); farthest
+            # point sampling is a serial chain per cloud (one CTA each) — 2B clouds in flight halve its wall time
+            B = pc1.shape[0]
+            (pa, fa), (pb, fb) = self._encode(torch.cat([pc1, pc2], 0), torch.cat([feature1, feature2], 0))
+            p1, f1, p2, f2 = pa[:B].contiguous(), fa[:B].contiguous(), pb[:B].contiguous(), fb[:B].contiguous()
+            q2, g2 = pb[B:].contiguous(), fb[B:].contiguous()
+        else:
+            (p1, f1), (p2, f2) = self._encode(pc1, feature1)            # frame 1 pyramid
+            _, (q2, g2) = self._encode(pc2, feature2)                    # frame 2, coarse level only
         _, mixed = self.fe_layer(p2, q2, f2, g2)                     # flow embedding at 256 points
         p3, f3 = self.sa3(p2, mixed)
         p4, f4 = self.sa4(p3, f3)
