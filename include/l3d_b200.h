@@ -353,6 +353,10 @@ int l3d_debug_soft_correspondence_scores(const float* src_emb_dev, const float* 
  * l3d_weighted_rigid_transform: compute_rigid_transform(a, b, weights) (rpmnet.py:221-254): a_dev, b_dev [B,M,3],
  * w_dev [B,M] -> T_dev [B,3,4] = [R | t], weighted Kabsch with the reference's determinant rule (third right
  * singular vector negated); eps = the reference's _EPS (1e-5, rpmnet.py:11) in w / (sum w + eps). */
+/* Row-wise top-k of a key matrix keys_dev [rows, N] already in HBM: idx_dev [rows, k] int64, largest key first,
+ * lower index on ties (the selection stage of l3d_knn_features).  knn_point() on C != 3 features
+ * (model_common_utils.py:84-100) = l3d_feature_square_distance + this on the negated distances. */
+int l3d_topk_rows(const float* keys_dev, long long rows, int N, int k, int64_t* idx_dev, void* stream);
 size_t l3d_feature_square_distance_ws_bytes(int B, int N, int M);
 int l3d_feature_square_distance(const float* src_dev, const float* dst_dev, int B, int N, int M, int C,
                                 const float* beta_dev, const float* alpha_dev, float* out_dev, void* ws_dev,
@@ -401,7 +405,7 @@ int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const floa
  *   out[b,m,p] = act(sum_k wt[k,m] * x[b,k,p] + bias[m]) (+ residual[b,m,p])     wt_dev = linear.weight.t() [K,M]
  * bias_dev / residual_dev may be NULL.  w_heads = h > 0 selects "one weight head per item" (the P.V product of
  * attention): x_dev holds B = batch*h items, wt_dev is [batch, K, h*M], item b uses columns (b % h)*M.. of weight
- * batch b / h, M must be 128.  Same shape requirements as l3d_conv1x1_bn_relu_maxk.
+ * batch b / h, M must be a multiple of 128.  Same shape requirements as l3d_conv1x1_bn_relu_maxk.
  *
  * l3d_attention_stats / l3d_attention_probs_t: softmax(q^T k / sqrt(D)) of transformer.py:17-23 in two passes of
  * the tcgen05 score pipeline (scores never written): q_dev [BH,D,Nq], k_dev [BH,D,Nk] (BH = batch*heads, the
@@ -411,6 +415,14 @@ int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const floa
  *
  * l3d_layernorm_cm: LayerNorm of transformer.py:128-137 over the channel axis of x_dev [B,D,N]:
  *   a2 * (x - mean) / (std_unbiased + eps) + b2. */
+/* Backward of l3d_soft_correspondence w.r.t. the scaled scores (DCP training, utils/svd.py:23-28 under autograd):
+ * dS[i,j] = P[i,j] (g_i . tgt_j - g_i . src_corr_i) / sqrt(D), P = softmax(src_emb^T tgt_emb / sqrt(D)) recomputed on
+ * tcgen05 from stats_dev (l3d_attention_stats); written plain (ds_dev [B,Ns,Nt]) and / or transposed
+ * (ds_t_dev [B,Nt,Ns]).  The embedding gradients follow as two l3d_linear_cm calls with per-item weights:
+ * d src_emb = tgt_emb . dS^T, d tgt_emb = src_emb . dS. */
+int l3d_soft_correspondence_dscores(const float* src_emb_dev, const float* tgt_emb_dev, const float* tgt_xyz_dev,
+                                    const float* stats_dev, const float* grad_corr_dev, const float* corr_dev, int B,
+                                    int D, int Ns, int Nt, float* ds_dev, float* ds_t_dev, void* stream);
 int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev, int B,
                   int M, int K, int P, int relu, int w_heads, float* out_dev, void* stream);
 int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, float* stats_dev,

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "l3d_debug_soft_correspondence_tiles": [_P],
     "l3d_debug_soft_correspondence_scores": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_chamfer_loss_fwd_bwd_host": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "l3d_topk_rows": [_P, ctypes.c_longlong, _I, _I, _P, _P],
     "l3d_feature_square_distance_ws_bytes": [_I, _I, _I],
     "l3d_feature_square_distance": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_sinkhorn_ws_bytes": [_I, _I, _I],
@@ -72,6 +73,7 @@ _SIGNATURES = {
     "l3d_edgeconv_layer1": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
     "l3d_conv1x1_bn_relu_maxk": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
     "l3d_edgeconv_status": [],
+    "l3d_soft_correspondence_dscores": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_linear_cm": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "l3d_attention_stats": [_P, _P, _I, _I, _I, _I, _P, _P],
     "l3d_attention_probs_t": [_P, _P, _P, _I, _I, _I, _I, _P, _P],

@@ -57,15 +57,6 @@ __device__ __forceinline__ float chamfer_d2(const float4 cc, float qx, float qy,
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Two queries per instruction (sm_100 FADD2 / FMUL2: per-lane IEEE rounding, so each half is bit-identical to
-// chamfer_d2): d2 of queries (a, b) against one candidate.  nq* hold the NEGATED query coordinates.
-__device__ __forceinline__ void chamfer_d2_x2(const float4 cc, unsigned long long nqx, unsigned long long nqy,
-                                              unsigned long long nqz, float& da, float& db) {
-  const unsigned long long dx = f2_add(f2_pack(cc.x, cc.x), nqx), dy = f2_add(f2_pack(cc.y, cc.y), nqy),
-                           dz = f2_add(f2_pack(cc.z, cc.z), nqz);
-  f2_unpack(f2_add(f2_add(f2_mul(dx, dx), f2_mul(dy, dy)), f2_mul(dz, dz)), da, db);
-}
-
 // grid = (query tiles, 2 directions, B).  A group of CH_LPQ lanes scans the candidates for Q queries at
 // once: every candidate float4 is loaded from shared memory once per Q queries and the Q distance
 // chains are independent (ILP) — Q = 4 for large batches, 1 when the grid would otherwise be too small.
@@ -97,16 +88,6 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFw
         qx[u] = q_xyz[qc * 3]; qy[u] = q_xyz[qc * 3 + 1]; qz[u] = q_xyz[qc * 3 + 2];
         best[u] = INFINITY; besti[u] = 0;
       }
-      // packed pairs of negated query coordinates (Q even): queries (2v, 2v+1) share every FADD2 / FMUL2
-      unsigned long long nqx[(Q + 1) / 2], nqy[(Q + 1) / 2], nqz[(Q + 1) / 2];
-      if (Q % 2 == 0) {
-#pragma unroll
-        for (int v2 = 0; v2 < Q / 2; ++v2) {
-          nqx[v2] = f2_pack(-qx[2 * v2], -qx[2 * v2 + 1]);
-          nqy[v2] = f2_pack(-qy[2 * v2], -qy[2 * v2 + 1]);
-          nqz[v2] = f2_pack(-qz[2 * v2], -qz[2 * v2 + 1]);
-        }
-      }
       bool have = false;
       for (int c = 0; c < nchunks; ++c) {
         const int c0 = c * CH_CHUNK;
@@ -130,20 +111,10 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_fwd_kernel(const ChamferFw
 #pragma unroll 4
         for (; j < cn; j += CH_LPQ) {
           const float4 cc = cand[j];
-          if (Q % 2 == 0) {
 #pragma unroll
-            for (int v2 = 0; v2 < Q / 2; ++v2) {
-              float da, db;
-              chamfer_d2_x2(cc, nqx[v2], nqy[v2], nqz[v2], da, db);
-              if (da < best[2 * v2]) { best[2 * v2] = da; besti[2 * v2] = c0 + j; }           // strict '<' (.cpp:78)
-              if (db < best[2 * v2 + 1]) { best[2 * v2 + 1] = db; besti[2 * v2 + 1] = c0 + j; }
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < Q; ++u) {
-              const float d = chamfer_d2(cc, qx[u], qy[u], qz[u]);
-              if (d < best[u]) { best[u] = d; besti[u] = c0 + j; }   // strict '<' (.cpp:78)
-            }
+          for (int u = 0; u < Q; ++u) {
+            const float d = chamfer_d2(cc, qx[u], qy[u], qz[u]);
+            if (d < best[u]) { best[u] = d; besti[u] = c0 + j; }   // strict '<' (.cpp:78)
           }
         }
       }

@@ -90,6 +90,10 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+// NOTE (measured on ptxas 12.9): a packed multiply feeding a packed add IS contracted into FFMA2 even with explicit
+// .rn on both instructions and -fmad=false, and fma(a, b, -0) is first simplified back to a multiply.  Code that
+// needs separately rounded products (Chamfer's (dx*dx + dy*dy) + dz*dz) therefore stays scalar; the packed helpers
+// are only used where the reference arithmetic itself is an fma chain (kNN expansion keys, EMD distances).
 __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));

@@ -538,7 +538,7 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
   if (B < 0 || M < 1 || K < 1 || P < 1 || G < 1) return L3D_ERR_INVALID;
   if (B == 0) return L3D_OK;
   if (!wt_dev || !x_dev || (!h_out_dev && !pool_out_dev) || w_heads < 0) return L3D_ERR_INVALID;
-  if (w_heads > 0 && (M != SC_BM || B % w_heads != 0)) return L3D_ERR_UNSUPPORTED;   // one 128-row block per head
+  if (w_heads > 0 && (M % SC_BM != 0 || B % w_heads != 0)) return L3D_ERR_UNSUPPORTED;   // whole 128-row blocks per head
   if (pool_out_dev && (P % G != 0 || G > EC_BN)) return L3D_ERR_INVALID;
   // TMA: 16-byte global strides and bases
   if ((P & 3) || (M & 3) || ((((uintptr_t)wt_dev) | ((uintptr_t)x_dev)) & 15)) return L3D_ERR_UNSUPPORTED;
@@ -634,7 +634,7 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
 // on the same tcgen05 pipeline (the transformer's nn.Linear layers with activations kept as [B, d_model, N]).
 // w_heads = 0: wt_dev [K, M] shared by all items.  w_heads = h > 0 ("one head per item", the P.V product of
 // attention): x_dev has B = batch*h items, wt_dev is [batch, K, h*M] and item b uses columns (b % h)*M.. of weight
-// batch b / h; M must be 128.
+// batch b / h; M must be a multiple of 128.
 extern "C" int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev,
                              int B, int M, int K, int P, int relu, int w_heads, float* out_dev, void* stream) {
   if (!out_dev) return L3D_ERR_INVALID;

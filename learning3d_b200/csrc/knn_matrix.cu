@@ -183,3 +183,14 @@ int knn_select_from_matrix(const float* keys, long rows, int N, int k, long long
 }
 
 }  // namespace l3d
+
+// Row-wise top-k of a key matrix that is already in HBM (largest key first, lower index on ties): the selection
+// stage of l3d_knn_features as an entry point of its own.  Used for knn_point() on C-dimensional features
+// (utils/model_common_utils.py:84-100 with C != 3): keys = -square_distance from l3d_feature_square_distance.
+extern "C" int l3d_topk_rows(const float* keys_dev, long long rows, int N, int k, int64_t* idx_dev, void* stream) {
+  if (rows < 0 || N < 1 || k < 1 || k > N) return L3D_ERR_INVALID;
+  if (rows == 0) return L3D_OK;
+  if (!keys_dev || !idx_dev) return L3D_ERR_INVALID;
+  return l3d::knn_select_from_matrix(keys_dev, (long)rows, N, k, reinterpret_cast<long long*>(idx_dev),
+                                     (cudaStream_t)stream);
+}

@@ -81,6 +81,11 @@ struct SoftCorrParams {
   // the TRANSPOSED probabilities P^T [B, Nt, Ns] (the B operand of the P.V GEMM, l3d_conv1x1_bn_relu_maxk)
   float* stats;           // [B, Ns, 2]: (running max in log2 units, sum of 2^(s - max))
   float* probs_t;         // [B, Nt, Ns]
+  // EPI_DS (backward of the soft correspondences): dS[i,j] = P[i,j] (g_i . tgt_j - g_i . corr_i) / sqrt(D)
+  const float* grad_corr; // [B, 3, Ns]  dL/d src_corr
+  const float* corr;      // [B, 3, Ns]  src_corr of the forward
+  float* ds;              // optional [B, Ns, Nt]
+  float* ds_t;            // optional [B, Nt, Ns]
   int kmajor;             // generic pipeline only: operands are [B, N, D] (channels contiguous) instead of [B, D, N]
   int* err;               // device error word (0 = ok)
   float* part;            // split target range only: partial softmax states [B, Ns, gridDim.z, 8]
@@ -165,6 +170,7 @@ __device__ __forceinline__ float sc_matrix_value(float v, float xa_i, float xb_j
 }
 constexpr int EPI_STATS = 3;         // attention pass 1: online (max, sum) of the scaled score rows -> stats [B,Ns,2]
 constexpr int EPI_PROBS_T = 4;       // attention pass 2: softmax probabilities, transposed -> probs_t [B,Nt,Ns]
+constexpr int EPI_DS = 5;            // SVD head backward: gradient of the scaled scores, plain and transposed
 constexpr int EPI_SOFTMAX_XYZ = 0;   // SVD head: online softmax, xyz-weighted sums  -> out [B,3,Ns]
 constexpr int EPI_KEYS = 1;          // feature-space kNN: negated expansion distances -> keys [B,Ns,Nt]
 
@@ -241,6 +247,17 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       pm = __ldg(p.stats + ((size_t)b * p.Ns + i) * 2);
       pinv = __fdividef(1.f, __ldg(p.stats + ((size_t)b * p.Ns + i) * 2 + 1));
     }
+    // EPI_DS: row statistics, upstream gradient of this row and its dot product with the forward output
+    float gx = 0.f, gy = 0.f, gz = 0.f, gc = 0.f, dscale = 0.f;
+    if (EPI == EPI_DS && i < p.Ns) {
+      pm = __ldg(p.stats + ((size_t)b * p.Ns + i) * 2);
+      pinv = __fdividef(1.f, __ldg(p.stats + ((size_t)b * p.Ns + i) * 2 + 1));
+      const float* g = p.grad_corr + (size_t)b * 3 * p.Ns + i;
+      const float* co = p.corr + (size_t)b * 3 * p.Ns + i;
+      gx = __ldg(g); gy = __ldg(g + p.Ns); gz = __ldg(g + 2 * (size_t)p.Ns);
+      gc = fmaf(gz, __ldg(co + 2 * (size_t)p.Ns), fmaf(gy, __ldg(co + p.Ns), gx * __ldg(co)));
+      dscale = c * 0.6931471805599453f;          // c = log2(e)/sqrt(D)  ->  1/sqrt(D)
+    }
     const bool aff = (EPI == EPI_SQDIST) && p.aff_beta != nullptr;
     const float a_beta = aff ? __ldg(p.aff_beta + b) : 0.f, a_alpha = aff ? __ldg(p.aff_alpha + b) : 0.f;
     bool ok = true;
@@ -308,6 +325,46 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (e < nv) dst[e] = sc_matrix_value<EPI>(v[e], xi, xz[e].x, a_beta, a_alpha, aff);
+          }
+          continue;
+        }
+        if (EPI == EPI_DS) {
+          // dS[i,j] = P[i,j] (g_i . tgt_j - g_i . corr_i) / sqrt(D); columns beyond Nt are never stored
+          const float4* xz = &sh->xyz[a][ch * 32];
+          const int nv = min(32, nvalid - ch * 32);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float pe = __fmul_rn(ex2_approx(fmaf(v[e], c, -pm)), pinv);
+            const float4 q = xz[e];
+            v[e] = pe * (fmaf(gz, q.z, fmaf(gy, q.y, gx * q.x)) - gc) * dscale;
+          }
+          if (p.ds_t && i < p.Ns) {
+            float* dst = p.ds_t + ((size_t)b * p.Nt + j0 + ch * 32) * p.Ns + i;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nv) dst[(size_t)e * p.Ns] = v[e];
+          }
+          if (p.ds) {
+            if (nv == 32 && (p.Nt & 3) == 0) {
+              float(*tb)[36] = sh->tbuf[warp];
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(&tb[lane][e]) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              __syncwarp();
+              const int rr = lane >> 3, cc = (lane & 7) * 4;
+              const int ibase = i0 + warp * 32;
+#pragma unroll
+              for (int r = 0; r < 32; r += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(&tb[r + rr][cc]);
+                const int ir = ibase + r + rr;
+                if (ir < p.Ns) *reinterpret_cast<float4*>(p.ds + ((size_t)b * p.Ns + ir) * p.Nt + j0 + ch * 32 + cc) = o;
+              }
+              __syncwarp();
+            } else if (i < p.Ns) {
+              float* dst = p.ds + ((size_t)b * p.Ns + i) * p.Nt + j0 + ch * 32;
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (e < nv) dst[e] = v[e];
+            }
           }
           continue;
         }
@@ -625,7 +682,7 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   }
   const long slots = pair ? sm_count / 2 : sm_count;   // 1 CTA per SM; a pair needs both SMs of a TPC
   int jsplit = 1;
-  if (EPI != EPI_STATS && g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
+  if (EPI != EPI_STATS && EPI != EPI_DS && g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
     jsplit = (int)((slots + units - 1) / units);
     if (g_softcorr_split > 0) jsplit = g_softcorr_split;
     if (jsplit > tiles) jsplit = tiles;
@@ -829,6 +886,27 @@ extern "C" int l3d_attention_probs_t(const float* q_dev, const float* k_dev, con
   p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = const_cast<float*>(stats_dev); p.probs_t = probs_t_dev;
   p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
   return sc_launch<EPI_PROBS_T>(p, stream);
+}
+
+// Backward of l3d_soft_correspondence w.r.t. the SCALED-score logits: with P = softmax(src_emb^T tgt_emb / sqrt(D)),
+// dS[i,j] = P[i,j] (g_i . tgt_j - g_i . src_corr_i) / sqrt(D) is written once plain (ds_dev [B,Ns,Nt]) and once
+// transposed (ds_t_dev [B,Nt,Ns]); either may be NULL.  The two embedding gradients are then plain GEMMs
+//   d src_emb = tgt_emb . dS^T,   d tgt_emb = src_emb . dS      (l3d_linear_cm with per-item weights).
+// stats_dev [B,Ns,2] comes from l3d_attention_stats(src_emb, tgt_emb).
+extern "C" int l3d_soft_correspondence_dscores(const float* src_emb, const float* tgt_emb, const float* tgt_xyz,
+                                               const float* stats_dev, const float* grad_corr_dev,
+                                               const float* corr_dev, int B, int D, int Ns, int Nt, float* ds_dev,
+                                               float* ds_t_dev, void* stream) {
+  if (B < 0 || D < 1 || Ns < 0 || Nt < 1) return L3D_ERR_INVALID;
+  if (B == 0 || Ns == 0) return L3D_OK;
+  if (!src_emb || !tgt_emb || !tgt_xyz || !stats_dev || !grad_corr_dev || !corr_dev || (!ds_dev && !ds_t_dev))
+    return L3D_ERR_INVALID;
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = src_emb; p.tgt_emb = tgt_emb; p.tgt_xyz = tgt_xyz; p.stats = const_cast<float*>(stats_dev);
+  p.grad_corr = grad_corr_dev; p.corr = corr_dev; p.ds = ds_dev; p.ds_t = ds_t_dev;
+  p.B = B; p.D = D; p.Ns = Ns; p.Nt = Nt;
+  return sc_launch<EPI_DS>(p, stream);
 }
 
 extern "C" int l3d_soft_correspondence(const float* src_emb, const float* tgt_emb, const float* tgt_xyz,

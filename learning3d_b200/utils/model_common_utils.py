@@ -119,10 +119,17 @@ def knn_point(k, pos1, pos2):
     pos2 = _C.require_cuda(pos2, "pos2")
     B, N, C = pos1.shape
     M = pos2.shape[1]
-    if C != 3 or pos2.shape[2] != 3:
-        raise NotImplementedError("learning3d_b200.knn_point: only C == 3 is built")
     if k > N:
         raise RuntimeError("selected index k out of range")
+    if C != 3 or pos2.shape[2] != 3:
+        # C-dimensional features: Gram matrix on the tensor cores, then the row-wise selection kernel (toleranced
+        # like every GEMM-based path; the reference evaluates the direct differences in fp32)
+        d2 = _ops.feature_square_distance(pos2, pos1)                 # [B, M, N]
+        keys = torch.neg(d2)
+        idx = torch.empty((B, M, k), dtype=torch.int64, device=pos1.device)
+        with _C.on_device(pos1.device):
+            _C.check(_C.lib().l3d_topk_rows(_C.ptr(keys), B * M, N, k, _C.ptr(idx), _C.stream()), "knn_point")
+        return torch.sqrt(torch.gather(d2, 2, idx).clamp_min_(0)), idx
     val = torch.empty((B, M, k), dtype=torch.float32, device=pos1.device)
     idx = torch.empty((B, M, k), dtype=torch.int64, device=pos1.device)
     with _C.on_device(pos1.device):

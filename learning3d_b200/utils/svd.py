@@ -3,8 +3,8 @@
 Same constructor, state_dict key (`reflect`) and forward contract.  The soft-correspondence front
 half (score GEMM, softmax, src_corr GEMM: svd.py:23-28) is ONE fused
 tcgen05 kernel (l3d_soft_correspondence: 3xTF32 score tiles in TMEM, online softmax, never writes the
-[B,N,N] score matrix) whenever no gradient is required; with autograd it stays on the reference's torch
-ops.  The tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
+[B,N,N] score matrix); under autograd the same forward is paired with a recompute-backward on tcgen05
+(_SoftCorr: row statistics + dS once, then two tensor-core GEMMs).  The tail — centring, H, the per-item torch.svd + torch.det loop with its host-synchronising
 branch (svd.py:38-51) and t — is ONE launch of l3d_svd_head_tail for the whole batch, and its backward
 (the reference trains through torch.svd's autograd) ONE launch of l3d_svd_head_tail_backward.
 """
@@ -65,6 +65,55 @@ def soft_correspondence(src_embedding, tgt_embedding, tgt):
     return out
 
 
+class _SoftCorr(torch.autograd.Function):
+    """Differentiable soft correspondences (svd.py:23-28) without the score matrix in the forward: the fused tcgen05
+    kernel computes src_corr; the backward recomputes the probabilities on tcgen05 from the row statistics, writes
+    dS (plain and transposed) once and finishes with two tensor-core GEMMs — no cuBLAS, no saved [B,N,N] tensors."""
+
+    @staticmethod
+    def forward(ctx, src_embedding, tgt_embedding, tgt):
+        corr = soft_correspondence(src_embedding, tgt_embedding, tgt)
+        ctx.save_for_backward(src_embedding, tgt_embedding, tgt, corr)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_corr):
+        src_emb, tgt_emb, tgt, corr = ctx.saved_tensors
+        lib = _C.lib()
+        B, D, Ns = src_emb.shape
+        Nt = tgt_emb.shape[2]
+        dev = src_emb.device
+        g = grad_corr.contiguous().float()
+        with _C.on_device(dev):
+            st = _C.stream()
+            stats = torch.empty((B, Ns, 2), dtype=torch.float32, device=dev)
+            _C.check(lib.l3d_attention_stats(_C.ptr(src_emb), _C.ptr(tgt_emb), B, D, Ns, Nt, _C.ptr(stats), st), "softcorr stats")
+            need_s, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            ds = torch.empty((B, Ns, Nt), dtype=torch.float32, device=dev) if need_t else None
+            ds_t = torch.empty((B, Nt, Ns), dtype=torch.float32, device=dev) if need_s else None
+            _C.check(lib.l3d_soft_correspondence_dscores(_C.ptr(src_emb), _C.ptr(tgt_emb), _C.ptr(tgt), _C.ptr(stats),
+                                                         _C.ptr(g), _C.ptr(corr), B, D, Ns, Nt, _C.ptr(ds), _C.ptr(ds_t),
+                                                         st), "softcorr dscores")
+            g_src = g_tgt = None
+            if need_s:          # d src_emb [B,D,Ns] = tgt_emb [D x Nt] . dS^T [Nt x Ns]
+                wt = tgt_emb.transpose(1, 2).contiguous()
+                g_src = torch.empty_like(src_emb)
+                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds_t), _C.ptr(None), _C.ptr(None), B, D, Nt, Ns, 0, 1,
+                                           _C.ptr(g_src), st), "softcorr d src_emb")
+            if need_t:          # d tgt_emb [B,D,Nt] = src_emb [D x Ns] . dS [Ns x Nt]
+                wt = src_emb.transpose(1, 2).contiguous()
+                g_tgt = torch.empty_like(tgt_emb)
+                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds), _C.ptr(None), _C.ptr(None), B, D, Ns, Nt, 0, 1,
+                                           _C.ptr(g_tgt), st), "softcorr d tgt_emb")
+        return g_src, g_tgt, None
+
+
+def _softcorr_trainable(src_embedding, tgt_embedding, tgt):
+    """The tensor-core backward needs TMA-friendly shapes and does not produce d tgt (the cloud itself)."""
+    D, Ns, Nt = src_embedding.shape[1], src_embedding.shape[2], tgt_embedding.shape[2]
+    return (not tgt.requires_grad) and D % 128 == 0 and Ns % 4 == 0 and Nt % 4 == 0
+
+
 def svd_head_tail(src, src_corr):
     """src, src_corr [B,3,N] (CUDA fp32) -> R [B,3,3], t [B,3]; differentiable."""
     return _SVDTail.apply(_C.require_cuda(src, "src"), _C.require_cuda(src_corr, "src_corr"))
@@ -88,6 +137,9 @@ class SVDHead(nn.Module):
         if not needs_grad:
             # inference: scores, softmax and the correspondence GEMM are one fused tcgen05 kernel
             src_corr = soft_correspondence(src_embedding, tgt_embedding, tgt)
+        elif _softcorr_trainable(src_embedding, tgt_embedding, tgt):
+            # training: same fused forward, recompute-backward on tcgen05 (no score matrix kept, no cuBLAS)
+            src_corr = _SoftCorr.apply(src_embedding.contiguous(), tgt_embedding.contiguous(), tgt.contiguous())
         else:
             # training: autograd needs the score matrix; same torch ops as the reference (svd.py:23-28)
             d_k = src_embedding.size(1)

@@ -20,6 +20,37 @@ def main(which):
         with torch.no_grad():
             for _ in range(2):
                 net(x)
+    elif which == "knn":
+        from learning3d_b200.utils import knn
+        x = torch.rand(32, 3, 1024, device=DEV)
+        for _ in range(5):
+            knn(x, 20)
+    elif which == "dcp":
+        from learning3d_b200.models import DCP, DGCNN
+        net = DCP(feature_model=DGCNN(emb_dims=512), cycle=True).to(DEV).eval()
+        a = torch.rand(32, 1024, 3, device=DEV); b = torch.rand(32, 1024, 3, device=DEV)
+        with torch.no_grad():
+            for _ in range(2):
+                net(a, b)
+                torch.cuda.synchronize()
+    elif which == "attn":
+        from learning3d_b200.utils.transformer import MultiHeadedAttention
+        from learning3d_b200.utils.transformer_fused import attention_cm
+        attn = MultiHeadedAttention(4, 512).to(DEV).eval()
+        x = torch.randn(32, 512, 1024, device=DEV)
+        with torch.no_grad():
+            for _ in range(2):
+                attention_cm(attn, x, x, x)
+    elif which == "rpm":
+        from learning3d_b200.models import rpmnet as R
+        from learning3d_b200.utils._ops import feature_square_distance
+        fs = 0.3 * torch.randn(8, 717, 96, device=DEV); fr = 0.3 * torch.randn(8, 717, 96, device=DEV)
+        beta = torch.ones(8, device=DEV); alpha = torch.full((8,), 0.5, device=DEV)
+        xyz = torch.rand(8, 717, 3, device=DEV)
+        for _ in range(2):
+            aff = feature_square_distance(fs, fr, beta, alpha)
+            perm, wt, rs = R.match_tail(aff, xyz, 5, True)
+            R.compute_rigid_transform(xyz, wt, rs)
     elif which == "emd":
         from learning3d_b200.losses import EMDLoss
         a = torch.rand(8, 1024, 3, device=DEV, requires_grad=True)

@@ -116,3 +116,19 @@ def test_square_distance_dispatch_and_reference_rpmnet_rebound():
     np.testing.assert_allclose(got[0].cpu().numpy(), want[0].cpu().numpy(), atol=1e-4)
     np.testing.assert_allclose(got[1].cpu().numpy(), want[1].cpu().numpy(), atol=2e-4)
     np.testing.assert_allclose(got[2].cpu().numpy(), want[2].cpu().numpy(), atol=2e-5)
+
+
+def test_knn_point_on_features():
+    """knn_point (model_common_utils.py:84-100) with C != 3: Gram matrix + selection; values sqrt(d2) within the GEMM
+    tolerance, indices equal the fp64 top-k wherever the k / k+1 gap exceeds it."""
+    from learning3d_b200.utils import knn_point
+    torch.manual_seed(2)
+    B, N, M, C, k = 2, 300, 120, 32, 9
+    data = torch.randn(B, N, C, device=DEV); query = torch.randn(B, M, C, device=DEV)
+    val, idx = knn_point(k, data, query)
+    d2 = ((query.double()[:, :, None, :] - data.double()[:, None, :, :]) ** 2).sum(-1)           # [B, M, N]
+    top = torch.topk(d2, k + 1, dim=-1, largest=False)
+    np.testing.assert_allclose(val.double().cpu().numpy(), top.values[..., :k].sqrt().cpu().numpy(), atol=2e-4)
+    clear = (top.values[..., k] - top.values[..., k - 1]) > 1e-3
+    same = (idx.sort(-1)[0] == top.indices[..., :k].sort(-1)[0]).all(-1)
+    assert same[clear].all() and clear.float().mean() > 0.9

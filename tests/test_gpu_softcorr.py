@@ -154,3 +154,43 @@ def test_target_range_split_and_merge(pipeline, split, B, D, Ns, Nt):
     assert not torch.isnan(out).any() and not torch.isnan(sc).any()
     assert ((sc.double() - s_ref).abs() <= 4e-6 * bound + 1e-30).all()
     assert (out.double() - o_ref).abs().max().item() <= 2e-5, (pipeline, split)
+
+
+@pytest.mark.parametrize("B,D,Ns,Nt", [(2, 128, 256, 256), (3, 512, 1024, 1024), (1, 256, 132, 520)])
+def test_soft_correspondence_backward_vs_fp64_autograd(B, D, Ns, Nt):
+    """_SoftCorr (fused forward + tcgen05 recompute-backward) against fp64 autograd of the reference's three lines
+    (utils/svd.py:23-28)."""
+    import math
+    from learning3d_b200.utils.svd import _SoftCorr
+    torch.manual_seed(B * D + Ns)
+    es = (0.3 * torch.randn(B, D, Ns, device="cuda")).requires_grad_(True)
+    et = (0.3 * torch.randn(B, D, Nt, device="cuda")).requires_grad_(True)
+    tgt = torch.rand(B, 3, Nt, device="cuda") - 0.5
+    w = torch.randn(B, 3, Ns, device="cuda")
+    corr = _SoftCorr.apply(es, et, tgt)
+    (corr * w).sum().backward()
+    es64 = es.detach().double().requires_grad_(True); et64 = et.detach().double().requires_grad_(True)
+    scores = torch.softmax(torch.matmul(es64.transpose(2, 1), et64) / math.sqrt(D), dim=2)
+    want = torch.matmul(tgt.double(), scores.transpose(2, 1))
+    (want * w.double()).sum().backward()
+    np.testing.assert_allclose(corr.detach().cpu().numpy(), want.detach().cpu().numpy(), atol=2e-5)
+    for got, ref, name in ((es.grad, es64.grad, "d src_emb"), (et.grad, et64.grad, "d tgt_emb")):
+        err = (got.double() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print("softcorr backward %s B=%d D=%d: max |err| = %.3g (|grad| max %.3g)" % (name, B, D, err, scale))
+        assert err <= 2e-5 * max(scale, 1e-3) + 1e-8
+
+
+def test_svd_head_training_path_uses_tensor_core_backward():
+    from learning3d_b200.utils import SVDHead
+    torch.manual_seed(9)
+    head = SVDHead(128).cuda()
+    es = torch.randn(2, 128, 256, device="cuda", requires_grad=True)
+    et = torch.randn(2, 128, 256, device="cuda", requires_grad=True)
+    src = torch.rand(2, 256, 3, device="cuda"); tgt = torch.rand(2, 256, 3, device="cuda")
+    from learning3d_b200 import _C
+    n0 = _C.launch_count()
+    R, t = head(es, et, src, tgt)
+    (R.sum() + t.sum()).backward()
+    assert _C.launch_count() - n0 >= 6          # fused forward, tail, tail backward, stats, dscores, 2 GEMMs
+    assert torch.isfinite(es.grad).all() and torch.isfinite(et.grad).all() and es.grad.abs().sum() > 0
