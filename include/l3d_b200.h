@@ -370,9 +370,10 @@ int l3d_rpm_match_tail(const float* affinity_dev, const float* xyz_ref_dev, int 
 int l3d_weighted_rigid_transform(const float* a_dev, const float* b_dev, const float* w_dev, int B, int M, float eps,
                                  float* T_dev, void* stream);
 
-/* Testing hook: nonzero makes l3d_emd_forward take the multi-launch path (21 kernels) instead of the persistent
- * cooperative launch (all 20 sweeps in one kernel with per-item barriers).  Both give identical results. */
-void l3d_debug_emd_force_multilaunch(int on);
+/* Testing hook for the forward path of l3d_emd_forward: 0 = default (ONE cooperative persistent launch runs all 20
+ * sweeps with per-item barriers), 1 = multi-launch (21 kernels), 2 = cooperative, 3 / 4 = one thread-block cluster
+ * of 16 / 8 CTAs per item (hardware cluster barriers).  All paths produce the same vectors. */
+void l3d_debug_emd_force_multilaunch(int mode);
 
 /* ---- EdgeConv stack of DGCNN (models/dgcnn.py:32-48, eval mode) ---------------------
  *

@@ -16,6 +16,8 @@ What is replaced (reference file:line -> ours):
   utils/transformer.py:255-263       Transformer.forward (eval: linear layers, attention, LayerNorm on tcgen05)
   models/dgcnn.py:25-49              DGCNN.forward    (eval mode: kNN graph + EdgeConv stack on tcgen05;
                                      training mode keeps the torch layers on the fused graph feature)
+  models/flownet3d.py:73-328         forward of PointNetSetAbstraction / FlowEmbedding / PointNetSetUpConv /
+                                     PointNetFeaturePropogation / FlowNet3D (eval: shared MLPs + max on tcgen05)
   models/rpmnet.py:130-254           match_features, sinkhorn, compute_rigid_transform (RPMNet's matching tail)
   utils/lib/pointnet2_utils.py:8     the `pointnet2_cuda` extension module
 Nothing is copied from the reference; only attributes of the live package objects are swapped.
@@ -27,6 +29,9 @@ _SAVED = {}     # id(pkg) -> list of (obj, attr, old)
 
 def _swap(rec, obj, attr, new):
     if not hasattr(obj, attr):
+        if attr.startswith("_"):                 # helper methods our forwards rely on (added, removed by unbind)
+            setattr(obj, attr, new)
+            rec.append((obj, attr, None))
         return
     rec.append((obj, attr, getattr(obj, attr)))
     setattr(obj, attr, new)
@@ -58,6 +63,25 @@ def bind(pkg, edgeconv=True):
         from .models import dgcnn as our_dgcnn
         if hasattr(our_dgcnn, "dgcnn_forward"):
             _swap(rec, dg.DGCNN, "forward", our_dgcnn.dgcnn_forward)
+    fl = sys.modules.get(pkg.__name__ + ".models.flownet3d")
+    if fl is not None and hasattr(fl, "FlowNet3D"):
+        # same attribute names as ours (the checkpoints force them), so our forward methods run on the reference's
+        # objects: grouping on the C ABI, shared MLPs + max on tcgen05 in eval mode, both frames batched
+        from .models import flownet3d as our_fl
+
+        def guarded(ours, theirs, ok):
+            def forward(self, *a, **k):
+                return ours(self, *a, **k) if ok(self) else theirs(self, *a, **k)
+            return forward
+        for name, ok in (("PointNetSetAbstraction", lambda m: True),
+                         ("FlowEmbedding", lambda m: m.knn and m.corr_func == "concat" and m.pooling == "max"),
+                         ("PointNetSetUpConv", lambda m: m.knn),
+                         ("PointNetFeaturePropogation", lambda m: True)):
+            cls = getattr(fl, name, None)
+            if cls is not None:
+                _swap(rec, cls, "forward", guarded(getattr(our_fl, name).forward, cls.forward, ok))
+        _swap(rec, fl.FlowNet3D, "_encode", our_fl.FlowNet3D._encode)
+        _swap(rec, fl.FlowNet3D, "forward", our_fl.FlowNet3D.forward)
     tr = sys.modules.get(pkg.__name__ + ".utils.transformer")
     if tr is not None and hasattr(tr, "Transformer"):
         from .utils.transformer_fused import transformer_forward

@@ -43,7 +43,7 @@ constexpr int EC_SPLIT_THREADS = 128;
 constexpr int EC_THREADS = EC_EPI_THREADS + EC_SPLIT_THREADS + 64 + EC_EPI_THREADS;
 constexpr int EC_BN = 256;           // positions per MMA (UMMA N)
 constexpr int EC_BK = 16;            // input channels per pipeline stage
-constexpr int EC_MAX_GROUPS = 16;    // pooled groups (points) per tile
+constexpr int EC_MAX_GROUPS = 32;    // pooled groups (points) per tile
 constexpr int EC_MAX_STAGES = 6;
 
 template <int CTAS>
@@ -531,6 +531,21 @@ extern "C" int l3d_edgeconv_layer1(const float* x_dev, const int64_t* idx_dev, c
 
 // relu(scale * (W . X) + shift) for X [B, K, P], W^T [K, M]; optional full output h_out [B, M, P] and optional max
 // over every group of G consecutive positions -> pool_out[b*pool_bstride + (pool_coff + c)*(P/G) + n].
+template <int GT>
+static cudaError_t edge_set_attrs_gt() {
+  cudaError_t e = cudaFuncSetAttribute(edge_gemm_kernel<1, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(edge_gemm_kernel<2, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
+}
+static cudaError_t edge_set_attrs() {
+  cudaError_t e = edge_set_attrs_gt<1>();
+  if (e == cudaSuccess) e = edge_set_attrs_gt<20>();
+  if (e == cudaSuccess) e = edge_set_attrs_gt<16>();
+  if (e == cudaSuccess) e = edge_set_attrs_gt<8>();
+  if (e == cudaSuccess) e = edge_set_attrs_gt<64>();
+  return e;
+}
+
 static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float* scale_dev, const float* shift_dev,
                             const float* residual_dev, int w_heads, int B, int M, int K, int P, int G, int relu,
                             float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
@@ -570,13 +585,7 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
     static uint64_t done_mask = 0;
     std::lock_guard<std::mutex> lock(mu);
     if (dev >= 64 || !(done_mask >> dev & 1)) {
-      cudaError_t e = cudaFuncSetAttribute(edge_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(edge_gemm_kernel<1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>());
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(edge_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
-      if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(edge_gemm_kernel<2, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>());
+      cudaError_t e = edge_set_attrs();
       if (e != cudaSuccess) return (int)e;
       if (dev < 64) done_mask |= (uint64_t)1 << dev;
     }
@@ -593,7 +602,7 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
   if (!wok || !make_dn_tmap(&mx, x_dev, B, K, P, EC_BK)) return L3D_ERR_UNSUPPORTED;
 
   const int sms = edge_sm_count(dev);
-  const bool fast20 = pool_out_dev != nullptr && G == 20 && p.TS == edge_tile_stride(20);
+  const int gt = (pool_out_dev != nullptr && (G == 20 || G == 16 || G == 8 || G == 64)) ? G : 1;
   if (pair) {
     long clusters = sms / 2;
     if (clusters > units) clusters = units;
@@ -606,15 +615,28 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    // DGCNN's k = 20 has a compile-time epilogue (static group boundaries); every other G runs the generic one
-    cudaError_t le = fast20 ? cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 20>, p, mw, mx)
-                            : cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 1>, p, mw, mx);
+    // group sizes with a compile-time epilogue (static group boundaries): DGCNN's k = 20, FlowNet3D's 8 / 16 / 64
+    cudaError_t le;
+    switch (gt) {
+      case 20: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 20>, p, mw, mx); break;
+      case 16: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 16>, p, mw, mx); break;
+      case 8: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 8>, p, mw, mx); break;
+      case 64: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 64>, p, mw, mx); break;
+      default: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 1>, p, mw, mx);
+    }
     if (le != cudaSuccess) return (int)le;
   } else {
     long grid = sms;
     if (grid > units) grid = units;
-    if (fast20) edge_gemm_kernel<1, 20><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
-    else edge_gemm_kernel<1, 1><<<(unsigned)grid, EC_THREADS, edge_smem_bytes<1>(), (cudaStream_t)stream>>>(p, mw, mx);
+    const size_t sm1 = edge_smem_bytes<1>();
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (gt) {
+      case 20: edge_gemm_kernel<1, 20><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
+      case 16: edge_gemm_kernel<1, 16><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
+      case 8: edge_gemm_kernel<1, 8><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
+      case 64: edge_gemm_kernel<1, 64><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
+      default: edge_gemm_kernel<1, 1><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx);
+    }
   }
   count_launch();
   L3D_LAUNCH_CHECK();

@@ -285,6 +285,175 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_persistent_kernel(const EmdPe
   }
 }
 
+// ---- cluster forward: one thread-block CLUSTER per batch item ------------------------------------------------------
+// The sweeps of an item only talk to each other, so an item is given to one cluster of up to 16 CTAs (one GPC's worth
+// of SMs; B = 8 fills the 8 GPCs of a B200): both clouds stay resident in every CTA's shared memory for the whole
+// kernel (only the 4-byte column weights are refreshed per sweep), the CTAs split the rows, and the 20 phase
+// boundaries are hardware cluster barriers (barrier.cluster, ~0.3 us) instead of global-memory counters.  Clusters
+// are independent, so nothing has to be co-resident across items: no cooperative launch, any B.
+constexpr int EMDC_THREADS = 512;
+constexpr int EMDC_WARPS = EMDC_THREADS / 32;
+constexpr int EMDC_RGROUPS = EMDC_WARPS / EMD_CSPLIT;          // 8 row groups of 4 rows per pass
+constexpr int EMDC_ROWS = EMDC_RGROUPS * EMD_R;
+
+struct EmdClusterSmem {
+  float part[EMD_CSPLIT][EMDC_RGROUPS][2 * EMD_R];
+};
+
+__device__ __forceinline__ void emd_cluster_barrier() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// rows [row_begin, row_end) of the row cloud (resident, float4 xyz_) against ALL columns of the column cloud
+// (resident, float4 xyz + current weight in .w); same arithmetic as emd_sweep_rows
+template <bool FUSED>
+__device__ __forceinline__ void emdc_sweep(const EmdSweepParams& p, int b, int row_begin, int row_end,
+                                           const float4* __restrict__ s_rows, float4* __restrict__ s_cols,
+                                           float* __restrict__ s_vb, EmdClusterSmem* sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp % EMDC_RGROUPS, ch = warp / EMDC_RGROUPS;
+  // refresh the column weights (written by other CTAs of the cluster in the previous phase: read through L2)
+  for (int c = tid; c < p.nc; c += EMDC_THREADS) {
+    s_cols[c].w = __ldcg(p.vA + (size_t)b * p.nc + c);
+    if (FUSED) s_vb[c] = __ldcg(p.vB + (size_t)b * p.nc + c);
+  }
+  __syncthreads();
+  const unsigned long long lvlA2 = f2_pack(p.lvlA, p.lvlA), lvlB2 = f2_pack(p.lvlB, p.lvlB), l2e2 = f2_pack(LOG2E, LOG2E);
+  for (int base = row_begin; base < row_end; base += EMDC_ROWS) {
+    const int r0 = base + rg * EMD_R;
+    unsigned long long nrx[2], nry[2], nrz[2], sa[2], sb[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 ra = s_rows[min(r0 + 2 * h, p.nr - 1)], rb = s_rows[min(r0 + 2 * h + 1, p.nr - 1)];
+      nrx[h] = f2_pack(-ra.x, -rb.x); nry[h] = f2_pack(-ra.y, -rb.y); nrz[h] = f2_pack(-ra.z, -rb.z);
+      sa[h] = 0ull; sb[h] = 0ull;
+    }
+    if (r0 < row_end) {
+      for (int c = ch * 32 + lane; c < p.nc; c += 32 * EMD_CSPLIT) {
+        const float4 q = s_cols[c];
+        const unsigned long long qx = f2_pack(q.x, q.x), qy = f2_pack(q.y, q.y), qz = f2_pack(q.z, q.z);
+        const unsigned long long qw = f2_pack(q.w, q.w);
+        unsigned long long vb2 = 0ull;
+        if (FUSED) { const float vb = s_vb[c]; vb2 = f2_pack(vb, vb); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned long long dx = f2_add(qx, nrx[h]), dy = f2_add(qy, nry[h]), dz = f2_add(qz, nrz[h]);
+          const unsigned long long d2 = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+          float t0, t1;
+          f2_unpack(f2_mul(f2_mul(lvlA2, d2), l2e2), t0, t1);
+          sa[h] = f2_fma(f2_pack(ex2_approx(t0), ex2_approx(t1)), qw, sa[h]);
+          if (FUSED) {
+            f2_unpack(f2_mul(f2_mul(lvlB2, d2), l2e2), t0, t1);
+            sb[h] = f2_fma(f2_pack(ex2_approx(t0), ex2_approx(t1)), vb2, sb[h]);
+          }
+        }
+      }
+    }
+    float fa[EMD_R], fb[EMD_R];
+    f2_unpack(sa[0], fa[0], fa[1]); f2_unpack(sa[1], fa[2], fa[3]);
+    f2_unpack(sb[0], fb[0], fb[1]); f2_unpack(sb[1], fb[2], fb[3]);
+#pragma unroll
+    for (int i = 0; i < EMD_R; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        fa[i] += __shfl_xor_sync(L3D_FULL_MASK, fa[i], o);
+        if (FUSED) fb[i] += __shfl_xor_sync(L3D_FULL_MASK, fb[i], o);
+      }
+    }
+    __syncthreads();                       // the previous pass has consumed sm->part
+    if (lane < EMD_R) {
+      float S = fa[0], S2 = fb[0];
+#pragma unroll
+      for (int i = 1; i < EMD_R; ++i) if (lane == i) { S = fa[i]; S2 = fb[i]; }
+      sm->part[ch][rg][lane] = S;
+      sm->part[ch][rg][EMD_R + lane] = S2;
+    }
+    __syncthreads();
+    if (ch == 0 && lane < EMD_R) {
+      float S = sm->part[0][rg][lane], S2 = sm->part[0][rg][EMD_R + lane];
+#pragma unroll
+      for (int k = 1; k < EMD_CSPLIT; ++k) { S += sm->part[k][rg][lane]; S2 += sm->part[k][rg][EMD_R + lane]; }
+      const int r = r0 + lane;
+      if (r < row_end && r < p.nr) {
+        const size_t o = (size_t)b * p.nr + r;
+        if (p.phase == EMD_PH1) {
+          const float rem = p.init ? p.multi : __ldcg(p.remain + o);
+          if (p.init) p.remain[o] = rem;
+          p.ratio_out[o] = rem / (1e-9f + S);
+        } else if (p.phase == EMD_PH2) {
+          const float rem = p.init ? p.multi : __ldcg(p.remain + o);
+          const float sumr = S * rem;
+          const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+          p.ratio_out[o] = consumption * rem;
+          p.remain[o] = fmaxf(0.0f, rem - sumr);
+        } else {
+          const float rem = fmaxf(0.0f, __ldcg(p.remain + o) - __ldcg(p.ratio_in + o) * S);
+          p.remain[o] = rem;
+          p.ratio_out[o] = rem / (1e-9f + S2);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EMDC_THREADS, 1) emd_cluster_kernel(const EmdPersistParams q) {
+  extern __shared__ __align__(16) unsigned char emdc_raw[];
+  float4* s_c1 = reinterpret_cast<float4*>(emdc_raw);                 // [n] cloud 1 (+ weight slot)
+  float4* s_c2 = s_c1 + q.n;                                           // [m] cloud 2
+  float* s_vb = reinterpret_cast<float*>(s_c2 + q.m);                  // [max(n, m)]
+  EmdClusterSmem* sm = reinterpret_cast<EmdClusterSmem*>(s_vb + max(q.n, q.m));
+  uint32_t NC, cx;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(NC));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cx));
+  const int b = blockIdx.x / NC;
+  const float* x1 = q.xyz1 + (size_t)b * q.n * 3;
+  const float* x2 = q.xyz2 + (size_t)b * q.m * 3;
+  for (int i = threadIdx.x; i < q.n; i += EMDC_THREADS) s_c1[i] = make_float4(x1[i * 3], x1[i * 3 + 1], x1[i * 3 + 2], 0.f);
+  for (int i = threadIdx.x; i < q.m; i += EMDC_THREADS) s_c2[i] = make_float4(x2[i * 3], x2[i * 3 + 1], x2[i * 3 + 2], 0.f);
+  auto share = [&](int nr, int& a0, int& a1) {
+    const int per = ((nr + (int)NC - 1) / (int)NC + EMD_R - 1) / EMD_R * EMD_R;
+    a0 = min(nr, (int)cx * per); a1 = min(nr, a0 + per);
+  };
+  int l0, l1, r0, r1;
+  share(q.n, l0, l1);
+  share(q.m, r0, r1);
+  const size_t Bn = (size_t)q.B * q.n, Bm = (size_t)q.B * q.m;
+  for (int r = r0 + (int)threadIdx.x; r < r1; r += EMDC_THREADS) q.remainR[(size_t)b * q.m + r] = q.multiR;
+  __syncthreads();
+  emd_cluster_barrier();
+  {
+    EmdSweepParams p{};
+    p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH1;
+    p.lvlA = q.lvl[0]; p.vA = q.remainR; p.remain = q.remainL; p.ratio_out = q.ratioL; p.multi = q.multiL; p.init = 1;
+    emdc_sweep<false>(p, b, l0, l1, s_c1, s_c2, s_vb, sm);
+  }
+  emd_cluster_barrier();
+  for (int it = 0; it < EMD_LEVELS; ++it) {
+    {
+      EmdSweepParams p{};
+      p.B = q.B; p.nr = q.m; p.nc = q.n; p.phase = EMD_PH2;
+      p.lvlA = q.lvl[it]; p.vA = q.ratioL + (size_t)it * Bn; p.remain = q.remainR; p.ratio_out = q.ratioR + (size_t)it * Bm;
+      emdc_sweep<false>(p, b, r0, r1, s_c2, s_c1, s_vb, sm);
+    }
+    if (it + 1 == EMD_LEVELS) break;
+    emd_cluster_barrier();
+    {
+      EmdSweepParams p{};
+      p.B = q.B; p.nr = q.n; p.nc = q.m; p.phase = EMD_PH3_PH1;
+      p.lvlA = q.lvl[it]; p.vA = q.ratioR + (size_t)it * Bm; p.lvlB = q.lvl[it + 1]; p.vB = q.remainR;
+      p.remain = q.remainL; p.ratio_in = q.ratioL + (size_t)it * Bn; p.ratio_out = q.ratioL + (size_t)(it + 1) * Bn;
+      emdc_sweep<true>(p, b, l0, l1, s_c1, s_c2, s_vb, sm);
+    }
+    emd_cluster_barrier();
+  }
+}
+
+static size_t emd_cluster_smem(int n, int m) {
+  return ((size_t)n + m) * sizeof(float4) + (size_t)std::max(n, m) * sizeof(float) + sizeof(EmdClusterSmem) + 16;
+}
+
 // Final pass: match[b, l, k] (reference index l*n + k, emd.cuh:158) = sum_j exp(level_j d2)
 // ratioL_j[k] ratioR_j[l]; cost[b] = sum match * |x1_k - x2_l|   (emd.cuh:201-244).
 // One warp per l (row of match), lanes over k: coalesced stores.  Deterministic two-level cost sum.
@@ -485,8 +654,9 @@ static int emd_slices(int B, int n, int m) {
 using namespace l3d;
 
 static int g_emd_force_multilaunch = 0;
-// Testing hook: nonzero forces the multi-launch (21 kernels) forward path instead of the persistent one.
-extern "C" void l3d_debug_emd_force_multilaunch(int on) { g_emd_force_multilaunch = on ? 1 : 0; }
+// Testing hook: 0 = default (cooperative persistent launch), 1 = multi-launch (21 kernels), 2 = cooperative,
+// 3 / 4 = one cluster of 16 / 8 CTAs per item (hardware cluster barriers, clouds resident in shared memory).
+extern "C" void l3d_debug_emd_force_multilaunch(int mode) { g_emd_force_multilaunch = (mode >= 0 && mode <= 4) ? mode : 0; }
 
 // workspace layout (floats): remainL[B,n] remainR[B,m] ratioL[LEVELS,B,n] ratioR[LEVELS,B,m]
 //                            partial[B*gx] | ticket[B] arrive[B] err[1] (uint)
@@ -526,8 +696,59 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
   EmdFinalParams fp{};
   for (int it = 0; it < EMD_LEVELS; ++it) fp.lvl[it] = emd_level(it);
 
+  // ---- cluster path: one cluster of 16 (else 8) CTAs per item, hardware cluster barriers ------------------------
+  bool clustered = false;
+  // mode 0 (default) = cooperative persistent launch; 3 / 4 = cluster kernel with 16 / 8 CTAs per item (measured
+  // slower at C5: 8 clusters of 16 one-CTA-per-SM blocks do not all fit at once, profiles/r02)
+  if ((g_emd_force_multilaunch == 3 || g_emd_force_multilaunch == 4) && emd_cluster_smem(n, m) <= 200 * 1024) {
+    static thread_local int c_dev = -1, c_nc = 0, c_mode = -1;
+    if (c_mode != g_emd_force_multilaunch) { c_dev = -1; c_mode = g_emd_force_multilaunch; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = emd_cluster_smem(n, m);
+    if (dev != c_dev) {
+      c_nc = 0;
+      cudaFuncSetAttribute(emd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(emd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      for (int nc = (g_emd_force_multilaunch == 3 ? 16 : 8); nc >= 8 && !c_nc; nc >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nc); cfg.blockDim = dim3(EMDC_THREADS); cfg.dynamicSmemBytes = 200 * 1024;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, emd_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1) c_nc = nc;
+      }
+      (void)cudaGetLastError();
+      c_dev = dev;
+    }
+    if (c_nc > 0) {
+      cudaError_t me = cudaMemsetAsync(ticket, 0, (2 * (size_t)B + 1) * sizeof(unsigned int), s);
+      if (me != cudaSuccess) return (int)me;
+      EmdPersistParams q{};
+      q.xyz1 = xyz1_dev; q.xyz2 = xyz2_dev; q.remainL = remainL; q.remainR = remainR; q.ratioL = ratioL; q.ratioR = ratioR;
+      q.arrive = arrive; q.err = errw; q.B = B; q.n = n; q.m = m; q.ctas_per_item = c_nc;
+      q.multiL = multiL; q.multiR = multiR;
+      for (int it = 0; it < EMD_LEVELS; ++it) q.lvl[it] = fp.lvl[it];
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(B * c_nc)); cfg.blockDim = dim3(EMDC_THREADS); cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = c_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, emd_cluster_kernel, q) == cudaSuccess) {
+        count_launch();
+        clustered = true;
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+  }
+
   // ---- persistent path: one cooperative launch runs all 20 sweeps (per-item barriers) ---------------------
-  bool persistent = g_emd_force_multilaunch == 0;
+  bool persistent = !clustered && g_emd_force_multilaunch != 1;
   int ctas_per_item = 0;
   if (persistent) {
     static thread_local int c_dev = -1, c_cap = 0;
@@ -566,7 +787,7 @@ extern "C" int l3d_emd_forward(const float* xyz1_dev, const float* xyz2_dev, int
       persistent = false;
     }
   }
-  if (!persistent) {
+  if (!persistent && !clustered) {
   {
     // remainR = multiR (emd.cuh:24-25) and zero the arrival tickets
     const long tot = (long)B * m;

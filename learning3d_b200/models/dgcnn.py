@@ -6,20 +6,7 @@ import torch.nn.functional as F
 
 from .. import _C
 from ..utils import get_graph_feature, knn
-
-
-def _fold_bn(conv, bn):
-    """Eval-mode BatchNorm folded into a per-channel (scale, shift) applied to the bias-free conv output."""
-    with torch.no_grad():
-        scale = torch.rsqrt(bn.running_var.float() + bn.eps)
-        if bn.weight is not None:
-            scale = scale * bn.weight.float()
-        shift = -bn.running_mean.float() * scale
-        if bn.bias is not None:
-            shift = shift + bn.bias.float()
-        if conv.bias is not None:
-            shift = shift + conv.bias.float() * scale
-    return scale.contiguous(), shift.contiguous()
+from ..utils.fused_mlp import fold_bn as _fold_bn
 
 
 def _edge_cache(net, dev):

@@ -7,7 +7,19 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..utils import fused_mlp
 from ..utils.lib import pointnet2_utils as pointutils
+
+
+def _mlp_max(feats, convs, bns, training):
+    """relu(bn(conv(.))) per level then max over the neighbour axis (models/flownet3d.py:115-121): in eval mode one
+    tcgen05 launch per level with BatchNorm folded, ReLU and the max in the epilogue; the torch layers otherwise."""
+    layers = list(zip(convs, bns))
+    if fused_mlp.usable(feats, layers, training):
+        return fused_mlp.mlp_forward(feats, layers, pool=True)
+    for conv, bn in layers:
+        feats = F.relu(bn(conv(feats)))
+    return torch.max(feats, -1)[0]
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
@@ -64,9 +76,7 @@ class PointNetSetAbstraction(nn.Module):
             fps_idx = pointutils.furthest_point_sample(xyz_t, self.npoint)
             new_xyz = pointutils.gather_operation(xyz.contiguous(), fps_idx)
         feats = self.queryandgroup(xyz_t, new_xyz.transpose(2, 1).contiguous(), points)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            feats = F.relu(bn(conv(feats)))
-        return new_xyz, torch.max(feats, -1)[0]
+        return new_xyz, _mlp_max(feats, self.mlp_convs, self.mlp_bns, self.training)
 
 
 class FlowEmbedding(nn.Module):
@@ -82,9 +92,7 @@ class FlowEmbedding(nn.Module):
         offsets, neighbours = _knn_groups(self.nsample, pos1, pos2, feature2)
         own = feature1.view(B, -1, N, 1).expand(-1, -1, -1, self.nsample)
         feat = torch.cat([offsets, neighbours, own], dim=1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
-            feat = F.relu(bn(conv(feat)))
-        return pos1, torch.max(feat, -1)[0]
+        return pos1, _mlp_max(feat, self.mlp_convs, self.mlp_bns, self.training)
 
 
 class PointNetSetUpConv(nn.Module):
@@ -108,11 +116,16 @@ class PointNetSetUpConv(nn.Module):
     def forward(self, pos1, pos2, feature1, feature2):
         offsets, neighbours = _knn_groups(self.nsample, pos1, pos2, feature2)
         feat = torch.cat([neighbours, offsets], dim=1)
-        for conv in self.mlp1_convs:
-            feat = conv(feat)
-        feat = feat.max(-1)[0]
+        if len(self.mlp1_convs) and fused_mlp.usable(feat, list(self.mlp1_convs), self.training):
+            feat = fused_mlp.mlp_forward(feat, list(self.mlp1_convs), pool=True)
+        else:
+            for conv in self.mlp1_convs:
+                feat = conv(feat)
+            feat = feat.max(-1)[0]
         if feature1 is not None:
             feat = torch.cat([feat, feature1], dim=1)
+        if len(self.mlp2_convs) and fused_mlp.usable(feat, list(self.mlp2_convs), self.training):
+            return fused_mlp.mlp_forward(feat, list(self.mlp2_convs))
         for conv in self.mlp2_convs:
             feat = conv(feat)
         return feat
@@ -138,7 +151,10 @@ class PointNetFeaturePropogation(nn.Module):
         feat = torch.sum(grouped * weight.view(B, 1, N, 3), dim=-1)
         if feature1 is not None:
             feat = torch.cat([feat, feature1], 1)
-        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+        layers = list(zip(self.mlp_convs, self.mlp_bns))
+        if fused_mlp.usable(feat, layers, self.training):
+            return fused_mlp.mlp_forward(feat, layers)
+        for conv, bn in layers:
             feat = F.relu(bn(conv(feat)))
         return feat
 
@@ -184,4 +200,7 @@ class FlowNet3D(nn.Module):
         up2 = self.su2(p2, p3, torch.cat([f2, mixed], dim=1), up3)
         up1 = self.su3(p1, p2, f1, up2)
         dense = self.fp(pc1, p1, feature1, up1)                      # back to the input resolution
-        return self.conv2(F.relu(self.bn1(self.conv1(dense))))
+        head = [(self.conv1, self.bn1)]
+        hidden = fused_mlp.mlp_forward(dense, head) if fused_mlp.usable(dense, head, self.training) \
+            else F.relu(self.bn1(self.conv1(dense)))
+        return self.conv2(hidden)

@@ -33,6 +33,16 @@ def main(which):
             for _ in range(2):
                 net(a, b)
                 torch.cuda.synchronize()
+    elif which == "flownet":
+        from learning3d_b200.models import FlowNet3D
+        fn = FlowNet3D().to(DEV).eval()
+        pc1 = torch.rand(16, 3, 2048, device=DEV) * 4 - 2
+        pc2 = pc1 + 0.05 * torch.randn_like(pc1)
+        f1 = torch.rand(16, 3, 2048, device=DEV); f2 = torch.rand(16, 3, 2048, device=DEV)
+        with torch.no_grad():
+            for _ in range(2):
+                fn(pc1, pc2, f1, f2)
+                torch.cuda.synchronize()
     elif which == "attn":
         from learning3d_b200.utils.transformer import MultiHeadedAttention
         from learning3d_b200.utils.transformer_fused import attention_cm

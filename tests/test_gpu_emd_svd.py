@@ -215,3 +215,32 @@ def test_emd_against_reference_cuda_kernels(B, n, m):
     torch.cuda.synchronize()
     np.testing.assert_allclose(g1.cpu().numpy(), rg1.cpu().numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(g2.cpu().numpy(), rg2.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,n,m", [(8, 1024, 1024), (3, 300, 700), (20, 512, 256), (1, 50, 33)])
+def test_emd_single_launch_paths_match_multilaunch(B, n, m):
+    """The single-launch forwards — cooperative persistent (default) and cluster-per-item with 16 / 8 CTAs (hardware
+    cluster barriers, clouds resident in shared memory) — against the 21-launch path: same arithmetic per pair, only
+    the partial-sum order inside a row differs."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    rng = np.random.default_rng(B * 7 + n)
+    a = T(rng.random((B, n, 3), dtype=np.float32)); b = T(rng.random((B, m, 3), dtype=np.float32))
+    outs = []
+    for force in (0, 1, 3, 4):
+        lib.l3d_debug_emd_force_multilaunch(force)
+        try:
+            cost = torch.empty((B,), device=DEV); match = torch.empty((B, n, m), device=DEV)
+            ws = torch.empty(int(lib.l3d_emd_forward_ws_bytes(B, n, m)), dtype=torch.uint8, device=DEV)
+            n0 = _C.launch_count()
+            _C.check(lib.l3d_emd_forward(_C.ptr(a), _C.ptr(b), B, n, m, _C.ptr(cost), _C.ptr(match), _C.ptr(ws), _C.stream()))
+            torch.cuda.synchronize()
+            outs.append((cost.cpu().numpy(), match.cpu().numpy(), _C.launch_count() - n0))
+        finally:
+            lib.l3d_debug_emd_force_multilaunch(0)
+    assert outs[0][2] == 2 and outs[1][2] == 22            # sweeps + final  vs  fill + 20 sweeps + final
+    assert outs[2][2] == 2 and outs[3][2] == 2              # cluster kernels: sweeps + final
+    for o in (outs[0], outs[2], outs[3]):
+        np.testing.assert_allclose(o[0], outs[1][0], rtol=2e-6)
+        np.testing.assert_allclose(o[1].sum(1), outs[1][1].sum(1), atol=2e-5)
+        np.testing.assert_allclose(o[1], outs[1][1], atol=5e-3)

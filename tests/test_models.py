@@ -87,3 +87,34 @@ def test_dcp_forward_matches_reference_fixture(golden_dir):
     R = out["est_R"].cpu().numpy()
     np.testing.assert_allclose(R @ R.transpose(0, 2, 1), np.tile(np.eye(3), (2, 1, 1)), atol=1e-5)
     assert out["r"].shape == (2, 32, 128)
+
+
+@pytest.mark.gpu
+def test_flownet3d_eval_fused_mlps_match_torch_layers():
+    """FlowNet3D in eval mode: shared MLPs + max over the neighbours on tcgen05 (BatchNorm folded) and both frames
+    batched through the encoder, against the same module with its torch layers (cuDNN fp32, TF32 off)."""
+    from learning3d_b200.models import FlowNet3D
+    from learning3d_b200.utils import fused_mlp
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(4)
+    net = FlowNet3D().cuda()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.1)
+    net.eval()
+    pc1 = torch.rand(4, 3, 2048, device="cuda") * 4 - 2
+    pc2 = pc1 + 0.05 * torch.randn_like(pc1)
+    f1 = torch.rand(4, 3, 2048, device="cuda"); f2 = torch.rand(4, 3, 2048, device="cuda")
+    with torch.no_grad():
+        got = net(pc1, pc2, f1, f2)
+        fused_mlp.ENABLED = False
+        try:
+            want = net(pc1, pc2, f1, f2)
+        finally:
+            fused_mlp.ENABLED = True
+    err = (got - want).abs().max().item()
+    print("FlowNet3D eval fused vs torch layers: max |diff| = %.3g (|flow| max %.3g)" % (err, want.abs().max().item()))
+    assert err <= 2e-5 * max(1.0, want.abs().max().item())
