@@ -460,30 +460,39 @@ __global__ void __launch_bounds__(256) edge_l1_kernel(const __grid_constant__ Ed
   for (int c = 0; c < EC_C1; ++c) o[(size_t)c * P] = edge_l1_value(W, c, nx, ny, nz, cx, cy, cz);
 }
 
-// thread = point n: max over its k neighbours of the same expression (bit-identical values), coalesced over n
-__global__ void __launch_bounds__(128) edge_l1_pool_kernel(const __grid_constant__ EdgeL1Weights W,
-                                                           const float* __restrict__ x, const long long* __restrict__ idx,
-                                                           int N, int k, float* __restrict__ pool, long pool_bstride,
-                                                           int pool_coff) {
+// thread = (point n, quarter of the channels): max over the point's k neighbours of the same expression
+// (bit-identical values), coalesced over n.  32 points x 4 channel quarters per CTA.
+constexpr int EC_L1P_Q = 4;
+__global__ void __launch_bounds__(32 * EC_L1P_Q) edge_l1_pool_kernel(const __grid_constant__ EdgeL1Weights W,
+                                                                     const float* __restrict__ x, const long long* __restrict__ idx,
+                                                                     int N, int k, float* __restrict__ pool, long pool_bstride,
+                                                                     int pool_coff) {
+  constexpr int CQ = EC_C1 / EC_L1P_Q;
   const int b = blockIdx.y;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int cq = threadIdx.x >> 5;
   if (n >= N) return;
   const float* xb = x + (size_t)b * 3 * N;
   const float cx = __ldg(xb + n), cy = __ldg(xb + N + n), cz = __ldg(xb + 2 * (size_t)N + n);
-  float m[EC_C1];
+  float m[CQ];
 #pragma unroll
-  for (int c = 0; c < EC_C1; ++c) m[c] = 0.f;                    // values are >= 0 after the ReLU
+  for (int c = 0; c < CQ; ++c) m[c] = 0.f;                      // values are >= 0 after the ReLU
   const long long* ip = idx + ((size_t)b * N + n) * k;
   for (int jj = 0; jj < k; ++jj) {
     long j = ip[jj];
     if ((unsigned long)j >= (unsigned long)N) j = n;
     const float nx = __ldg(xb + j), ny = __ldg(xb + N + j), nz = __ldg(xb + 2 * (size_t)N + j);
 #pragma unroll
-    for (int c = 0; c < EC_C1; ++c) m[c] = fmaxf(m[c], edge_l1_value(W, c, nx, ny, nz, cx, cy, cz));
-  }
-  float* o = pool + (size_t)b * pool_bstride + (size_t)pool_coff * N + n;
+    for (int q = 0; q < EC_L1P_Q; ++q) {
+      if (q == cq) {                                             // warp-uniform: weights stay constant-bank operands
 #pragma unroll
-  for (int c = 0; c < EC_C1; ++c) o[(size_t)c * N] = m[c];
+        for (int c = 0; c < CQ; ++c) m[c] = fmaxf(m[c], edge_l1_value(W, q * CQ + c, nx, ny, nz, cx, cy, cz));
+      }
+    }
+  }
+  float* o = pool + (size_t)b * pool_bstride + (size_t)(pool_coff + cq * CQ) * N + n;
+#pragma unroll
+  for (int c = 0; c < CQ; ++c) o[(size_t)c * N] = m[c];
 }
 
 }  // namespace l3d
@@ -521,7 +530,7 @@ extern "C" int l3d_edgeconv_layer1(const float* x_dev, const int64_t* idx_dev, c
     L3D_LAUNCH_CHECK();
   }
   if (pool_dev) {
-    edge_l1_pool_kernel<<<dim3((unsigned)((N + 127) / 128), B), 128, 0, (cudaStream_t)stream>>>(
+    edge_l1_pool_kernel<<<dim3((unsigned)((N + 31) / 32), B), 32 * EC_L1P_Q, 0, (cudaStream_t)stream>>>(
         W, x_dev, reinterpret_cast<const long long*>(idx_dev), N, k, pool_dev, (long)pool_bstride, pool_coff);
     count_launch();
     L3D_LAUNCH_CHECK();
