@@ -316,9 +316,11 @@ def run_ours(args, rank, local_rank, world):
                          "note": "fp32-issue/selection bound once the NxN matrix is not materialised "
                                  "(SURVEY.md §8d): a perfect kernel reaches ~20% of HBM peak at this shape"},
             "e2e": {"value": world * B * N * N * e2e_steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * N * k * 2,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "path": "l3d_knn_expansion_host (pinned host buffers, H2D + kernel + D2H + sync)"},
+                    "path": "l3d_knn_expansion_host: host fp32 cloud in, host int64 indices out; H2D, kernel and D2H "
+                            "inside (indices cross PCIe as uint16 and are widened to the caller's int64 array by "
+                            "host threads while later slices are in flight), one sync"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }

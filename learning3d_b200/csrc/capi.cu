@@ -3,8 +3,10 @@
 #include "common.cuh"
 #include "../../include/l3d_b200.h"
 #include "launch_count.h"
+#include "knn_matrix.h"
 
 #include <atomic>
+#include <omp.h>
 #include <cstdlib>
 #include <mutex>
 
@@ -54,69 +56,78 @@ extern "C" uint64_t l3d_launch_count(void) {
   return l3d::g_launches.load(std::memory_order_relaxed);
 }
 
+// knn() from HOST buffers.  The call is PCIe-bound on its OUTPUT: 8*k bytes of int64 indices return per 12 bytes of
+// input (5.2 MB per C2 batch, ~100 us of D2H at the ~50 GB/s a pinned copy reaches), three times the kernel.  Every
+// index is < N <= 8192, so the device writes uint16, 2 bytes per index cross the bus (1.3 MB) into an internal pinned
+// staging buffer, and the host widens them to the caller's int64 array with a few OpenMP threads while the next
+// slice is still in flight.  The batch is cut into slices that ping-pong over two streams (clouds are independent).
 extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, int64_t* idx_host) {
   if (!x_host || !idx_host || B < 0 || N < 1 || k < 1 || k > N) return L3D_ERR_INVALID;
   if (B == 0) return L3D_OK;
   std::lock_guard<std::mutex> lock(l3d::g_host.mu);
   const size_t in_bytes = (size_t)B * 3 * N * sizeof(float);
-  const size_t out_bytes = (size_t)B * N * k * sizeof(int64_t);
-  int rc = l3d::g_host.ensure(in_bytes, out_bytes);
+  const size_t n_idx = (size_t)B * N * k;
+  int rc = l3d::g_host.ensure(in_bytes, n_idx * sizeof(unsigned short));
   if (rc) return rc;
-  // Zero-copy output (L3D_KNN_HOST_ZEROCOPY=1, experiment): when idx_host is pinned, the kernel stores the
-  // indices straight into host memory over PCIe, so the write-back overlaps the whole kernel instead of
-  // following it.  Measured on the B200 box: see DESIGN.md §7 before enabling by default.
-  static int zero_copy = -1;
-  if (zero_copy < 0) {
-    const char* ev = getenv("L3D_KNN_HOST_ZEROCOPY");
-    zero_copy = (ev && ev[0] == '1') ? 1 : 0;
-  }
-  if (zero_copy) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, idx_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
-        at.devicePointer) {
-      cudaStream_t s = l3d::g_host.stream;
-      cudaError_t ze = cudaMemcpyAsync(l3d::g_host.in, x_host, in_bytes, cudaMemcpyHostToDevice, s);
-      if (ze) return (int)ze;
-      rc = l3d_knn_expansion((const float*)l3d::g_host.in, B, N, k, (int64_t*)at.devicePointer, nullptr, s);
-      if (rc) return rc;
-      return (int)cudaStreamSynchronize(s);
-    }
-    cudaGetLastError();   // not a pinned buffer: fall through to the copy pipeline
-  }
-  // The call is PCIe-bound: 8*k bytes of int64 indices return per 12 bytes of input.  The batch is
-  // cut into slices that ping-pong over two streams so the device-to-host copy of slice i overlaps
-  // the kernel of slice i+1 (clouds are independent; each slice is a whole number of clouds).
   cudaError_t e;
+  // grow-only pinned staging buffer for the narrow indices
+  static unsigned short* stage = nullptr;
+  static size_t stage_cap = 0;
+  if (n_idx > stage_cap) {
+    if (stage) cudaFreeHost(stage);
+    stage = nullptr; stage_cap = 0;
+    e = cudaHostAlloc((void**)&stage, n_idx * sizeof(unsigned short), cudaHostAllocDefault);
+    if (e) return (int)e;
+    stage_cap = n_idx;
+  }
   if (!l3d::g_host.stream2) {
     e = cudaStreamCreateWithFlags(&l3d::g_host.stream2, cudaStreamNonBlocking);
     if (e) return (int)e;
   }
+  constexpr int MAX_SLICES = 8;
+  static cudaEvent_t ev[MAX_SLICES] = {};
   cudaStream_t st[2] = {l3d::g_host.stream, l3d::g_host.stream2};
-  const int nslice = B >= 8 ? 4 : (B >= 2 ? 2 : 1);
+  const int nslice = B >= 16 ? 8 : (B >= 8 ? 4 : (B >= 2 ? 2 : 1));
   const float* din = (const float*)l3d::g_host.in;
-  int64_t* dout = (int64_t*)l3d::g_host.out;
-  int b0 = 0;
+  unsigned short* dout = (unsigned short*)l3d::g_host.out;
+  int bounds[MAX_SLICES + 1];
+  for (int i = 0; i <= nslice; ++i) bounds[i] = (int)((long)B * i / nslice);
   for (int i = 0; i < nslice; ++i) {
-    const int b1 = (int)((long)B * (i + 1) / nslice);
-    const int nb = b1 - b0;
+    const int b0 = bounds[i], nb = bounds[i + 1] - b0;
+    if (!ev[i]) { e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e) return (int)e; }
+    cudaStream_t s = st[i & 1];
+    const size_t io = (size_t)b0 * 3 * N, oo = (size_t)b0 * N * k;
     if (nb > 0) {
-      cudaStream_t s = st[i & 1];
-      const size_t io = (size_t)b0 * 3 * N, oo = (size_t)b0 * N * k;
-      e = cudaMemcpyAsync((void*)(din + io), x_host + io, (size_t)nb * 3 * N * sizeof(float),
-                          cudaMemcpyHostToDevice, s);
+      e = cudaMemcpyAsync((void*)(din + io), x_host + io, (size_t)nb * 3 * N * sizeof(float), cudaMemcpyHostToDevice, s);
       if (e) return (int)e;
-      rc = l3d_knn_expansion(din + io, nb, N, k, dout + oo, nullptr, s);
+      rc = l3d::knn_expansion_u16(din + io, nb, N, k, dout + oo, s);
       if (rc) return rc;
-      e = cudaMemcpyAsync(idx_host + oo, dout + oo, (size_t)nb * N * k * sizeof(int64_t),
-                          cudaMemcpyDeviceToHost, s);
+      e = cudaMemcpyAsync(stage + oo, dout + oo, (size_t)nb * N * k * sizeof(unsigned short), cudaMemcpyDeviceToHost, s);
       if (e) return (int)e;
     }
-    b0 = b1;
+    e = cudaEventRecord(ev[i], s);
+    if (e) return (int)e;
   }
-  e = cudaStreamSynchronize(st[0]);
-  if (e) return (int)e;
-  e = cudaStreamSynchronize(st[1]);
-  return (int)e;
+  // widen slice by slice as the copies land
+  static int nthreads = 0;
+  if (nthreads == 0) {
+    const char* ev_t = getenv("L3D_HOST_THREADS");
+    nthreads = ev_t ? atoi(ev_t) : 8;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > omp_get_max_threads()) nthreads = omp_get_max_threads();
+  }
+  for (int i = 0; i < nslice; ++i) {
+    e = cudaEventSynchronize(ev[i]);
+    if (e) return (int)e;
+    const long i0 = (long)bounds[i] * N * k, i1 = (long)bounds[i + 1] * N * k;
+    const unsigned short* src = stage;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long c = i0 / 4096; c < (i1 + 4095) / 4096; ++c) {
+      const long a = c * 4096 < i0 ? i0 : c * 4096, z = (c + 1) * 4096 > i1 ? i1 : (c + 1) * 4096;
+      for (long t = a; t < z; ++t) idx_host[t] = (int64_t)src[t];
+    }
+  }
+  return L3D_OK;
 }
 
 // Chamfer loss + both gradients from HOST buffers in one call (the "Chamfer fwd+bwd" half of the headline metric

@@ -78,7 +78,7 @@ struct KnnParams {
   float* out_val;      // optional [B,M,k]
   float* feat_out;     // optional [B,6,N,k] graph feature (knn() on xyz only: SELF, [B,3,N] input)
   int B, N, M, k;
-  int idx64;      // 1 -> int64 indices, 0 -> int32
+  int idx64;      // 1 -> int64 indices, 0 -> int32, 2 -> uint16 (host-buffer path: narrow on the PCIe wire)
   int val_xform;  // 0: key, 1: -key, 2: sqrt(-key)
   int use_tma;    // alignment preconditions for cp.async.bulk hold
   int force_slow;
@@ -142,6 +142,12 @@ __device__ __forceinline__ float4 knn_padding() {
   return make_float4(INFINITY, INFINITY, INFINITY, 0.f);
 }
 
+__device__ __forceinline__ void knn_store_index(const KnnParams& p, long o, uint32_t ix) {
+  if (p.idx64 == 1) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)ix;
+  else if (p.idx64 == 0) reinterpret_cast<int*>(p.out_idx)[o] = (int)ix;
+  else reinterpret_cast<unsigned short*>(p.out_idx)[o] = (unsigned short)ix;
+}
+
 __device__ __forceinline__ float knn_val_xform(float key, int xform) {
   // 0 - key (not -key): a zero distance comes out as +0.0 like the reference's
   if (xform == 1) return 0.0f - key;
@@ -172,8 +178,7 @@ __device__ __noinline__ void knn_row_slow(const KnnParams& p, const float4* __re
     }
     if (lane == 0) {
       const long o = row * p.k + r;
-      if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)bi;
-      else reinterpret_cast<int*>(p.out_idx)[o] = (int)bi;
+      knn_store_index(p, o, bi);
       if (p.out_val) p.out_val[o] = knn_val_xform(bv, p.val_xform);
     }
     pv = bv; pi = bi; first = false;
@@ -188,8 +193,7 @@ __device__ __forceinline__ void knn_store(const KnnParams& p, long row, int lane
     const int pos = s * 32 + lane;
     if (pos < p.k) {
       const long o = row * p.k + pos;
-      if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)ix[s];
-      else reinterpret_cast<int*>(p.out_idx)[o] = (int)ix[s];
+      knn_store_index(p, o, ix[s]);
       if (p.out_val) p.out_val[o] = knn_val_xform(v[s], p.val_xform);
     }
   }
@@ -335,8 +339,7 @@ __device__ __forceinline__ void knn_store_packed(const KnnParams& p, long row, i
   if (pos < p.k) {
     const long o = row * p.k + pos;
     const uint32_t ix = ~(uint32_t)c;
-    if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = (long long)ix;
-    else reinterpret_cast<int*>(p.out_idx)[o] = (int)ix;
+    knn_store_index(p, o, ix);
     if (p.out_val) p.out_val[o] = knn_val_xform(f32_unorder((uint32_t)(c >> 32)), p.val_xform);
   }
 }
@@ -907,6 +910,17 @@ extern "C" int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_
   p.B = B; p.N = N; p.M = N; p.k = k; p.idx64 = 1; p.val_xform = 0;
   return knn_launch<MODE_EXPANSION_NEG, true, true>(p, (cudaStream_t)stream);
 }
+
+// knn() with 16-bit indices (N <= 65536 always holds: N <= L3D_KNN_MAX_N): the device half of
+// l3d_knn_expansion_host, which moves 2 instead of 8 bytes per index over PCIe and widens on the host.
+namespace l3d {
+int knn_expansion_u16(const float* x_dev, int B, int N, int k, unsigned short* idx_dev, cudaStream_t stream) {
+  KnnParams p{};
+  p.cand = x_dev; p.query = nullptr; p.out_idx = idx_dev; p.out_val = nullptr;
+  p.B = B; p.N = N; p.M = N; p.k = k; p.idx64 = 2; p.val_xform = 0;
+  return knn_launch<MODE_EXPANSION_NEG, true, true>(p, stream);
+}
+}  // namespace l3d
 
 extern "C" int l3d_knn_graph_feature(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
                                      float* feat_dev, void* stream) {
