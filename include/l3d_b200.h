@@ -124,7 +124,7 @@ int l3d_knn_sqdist(const float* xyz_dev, const float* new_xyz_dev, int B, int N,
  *   unknown_dev [b,n,3] queries, known_dev [b,m,3] data,
  *   dist2_dev [b,n,k] fp32 squared distance ascending, idx_dev [b,n,k] int32.
  * d2 = fma(dz,dz, fma(dy,dy, dx*dx))  (nvcc's contraction of the reference expression).
- * k <= 128 here (the reference allows 200).
+ * k <= 128 runs the threshold + sorting-network selection; larger k (the reference allows 200) the exact k-round scan.
  */
 int l3d_pn2_knn(int b, int n, int m, int k, const float* unknown_dev, const float* known_dev,
                 float* dist2_dev, int32_t* idx_dev, void* stream);

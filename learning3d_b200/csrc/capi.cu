@@ -60,7 +60,9 @@ extern "C" uint64_t l3d_launch_count(void) {
 // input (5.2 MB per C2 batch, ~100 us of D2H at the ~50 GB/s a pinned copy reaches), three times the kernel.  Every
 // index is < N <= 8192, so the device writes uint16, 2 bytes per index cross the bus (1.3 MB) into an internal pinned
 // staging buffer, and the host widens them to the caller's int64 array with a few OpenMP threads while the next
-// slice is still in flight.  The batch is cut into slices that ping-pong over two streams (clouds are independent).
+// slice is still in flight.  The batch is cut into (by default two) slices on two streams (clouds are independent);
+// more slices overlap better on paper but every slice costs four driver calls, and those ~4 us each are what the
+// call is bound by once the bytes are narrow (C2: 171 us with int64 over the bus and 4 slices -> 104 us).
 extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, int64_t* idx_host) {
   if (!x_host || !idx_host || B < 0 || N < 1 || k < 1 || k > N) return L3D_ERR_INVALID;
   if (B == 0) return L3D_OK;
@@ -87,7 +89,15 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   constexpr int MAX_SLICES = 8;
   static cudaEvent_t ev[MAX_SLICES] = {};
   cudaStream_t st[2] = {l3d::g_host.stream, l3d::g_host.stream2};
-  const int nslice = B >= 16 ? 8 : (B >= 8 ? 4 : (B >= 2 ? 2 : 1));
+  static int slice_cap = 0;
+  if (slice_cap == 0) {
+    const char* ev_s = getenv("L3D_HOST_SLICES");
+    slice_cap = ev_s ? atoi(ev_s) : 2;     // measured at C2 (profiles/r02): 1 / 2 / 4 / 8 slices = 130 / 104 / 118 / 157 us
+    if (slice_cap < 1) slice_cap = 1;
+    if (slice_cap > MAX_SLICES) slice_cap = MAX_SLICES;
+  }
+  int nslice = B >= 16 ? 8 : (B >= 8 ? 4 : (B >= 2 ? 2 : 1));
+  if (nslice > slice_cap) nslice = slice_cap;
   const float* din = (const float*)l3d::g_host.in;
   unsigned short* dout = (unsigned short*)l3d::g_host.out;
   int bounds[MAX_SLICES + 1];
@@ -112,7 +122,7 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   static int nthreads = 0;
   if (nthreads == 0) {
     const char* ev_t = getenv("L3D_HOST_THREADS");
-    nthreads = ev_t ? atoi(ev_t) : 8;
+    nthreads = ev_t ? atoi(ev_t) : 4;      // 1 / 2 / 4 / 8 / 16 threads at 8 slices: 253 / 190 / 158 / 159 / 157 us
     if (nthreads < 1) nthreads = 1;
     if (nthreads > omp_get_max_threads()) nthreads = omp_get_max_threads();
   }

@@ -653,7 +653,7 @@ static int emd_slices(int B, int n, int m) {
 
 using namespace l3d;
 
-static int g_emd_force_multilaunch = 0;
+static thread_local int g_emd_force_multilaunch = 0;   // per host thread: a test toggling it cannot affect launches of other threads
 // Testing hook: 0 = default (cooperative persistent launch), 1 = multi-launch (21 kernels), 2 = cooperative,
 // 3 / 4 = one cluster of 16 / 8 CTAs per item (hardware cluster barriers, clouds resident in shared memory).
 extern "C" void l3d_debug_emd_force_multilaunch(int mode) { g_emd_force_multilaunch = (mode >= 0 && mode <= 4) ? mode : 0; }

@@ -607,10 +607,10 @@ static bool make_emb_tmap(CUtensorMap* m, const float* emb, int B, int D, int N)
 
 using namespace l3d;
 
-static int g_softcorr_force_generic = 0;
+static thread_local int g_softcorr_force_generic = 0;   // testing hooks are per host thread
 
 // -1: never split the target range, 0: automatic (small batches), > 0: forced number of splits (testing hook)
-static int g_softcorr_split = 0;
+static thread_local int g_softcorr_split = 0;
 
 // Combines the partial softmax states of a split target range: state z = (m_z in log2 units, l_z, a_z[3]);
 // out = sum_z a_z 2^(m_z - M) / sum_z l_z 2^(m_z - M), M = max_z m_z.

@@ -51,8 +51,8 @@ def test_maximum_cloud_size_and_beyond(oracle_mod):
     assert np.array_equal(knn(T(x), 20).cpu().numpy(), oracle_mod.knn_expansion(x, 20, mt=True))
     with pytest.raises(RuntimeError, match="not supported"):
         knn(torch.rand(1, 3, 8196, device=DEV), 4)
-    with pytest.raises(RuntimeError, match="not supported"):
-        knn(torch.rand(1, 3, 1024, device=DEV), 129)                 # k > 128
+    y = rng.random((1, 3, 700), dtype=np.float32)                    # k > 128: exact k-round scan path
+    assert np.array_equal(knn(T(y), 200).cpu().numpy(), oracle_mod.knn_expansion(y, 200, mt=True))
 
 
 def test_k_ranges_take_every_kernel_variant(oracle_mod):
