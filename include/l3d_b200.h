@@ -404,14 +404,17 @@ int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const floa
  *
  * l3d_linear_cm: nn.Linear on channel-major activations, tcgen05 3xTF32:
  *   out[b,m,p] = act(sum_k wt[k,m] * x[b,k,p] + bias[m]) (+ residual[b,m,p])     wt_dev = linear.weight.t() [K,M]
- * bias_dev / residual_dev may be NULL.  w_heads = h > 0 selects "one weight head per item" (the P.V product of
+ * bias_dev / residual_dev / col_div_dev may be NULL; col_div_dev [B,P] divides every output column (after bias and
+ * activation, before the residual).  w_heads = h > 0 selects "one weight head per item" (the P.V product of
  * attention): x_dev holds B = batch*h items, wt_dev is [batch, K, h*M], item b uses columns (b % h)*M.. of weight
  * batch b / h, M must be a multiple of 128.  Same shape requirements as l3d_conv1x1_bn_relu_maxk.
  *
  * l3d_attention_stats / l3d_attention_probs_t: softmax(q^T k / sqrt(D)) of transformer.py:17-23 in two passes of
  * the tcgen05 score pipeline (scores never written): q_dev [BH,D,Nq], k_dev [BH,D,Nk] (BH = batch*heads, the
  * [B, h*d_k, N] projections viewed per head) -> stats_dev [BH,Nq,2] (row max in log2 units, row sum) and then
- * probs_t_dev [BH,Nk,Nq], the probabilities TRANSPOSED — exactly the activation operand l3d_linear_cm(w_heads)
+ * probs_t_dev [BH,Nk,Nq], the probabilities TRANSPOSED.  Fast protocol: stats with precise = 0 (ONE TF32 pass: the
+ * max only serves as exponent reference), probs with normalized = 0 (writes 2^(s - max) and stores the exact row
+ * sums into stats_dev[..,1]), then l3d_linear_cm(..., col_div_dev = those sums).  The result is — exactly the activation operand l3d_linear_cm(w_heads)
  * needs for out[bh, d_v, q] = sum_k v^T[k, d_v] p^T[k, q].
  *
  * l3d_layernorm_cm: LayerNorm of transformer.py:128-137 over the channel axis of x_dev [B,D,N]:
@@ -424,12 +427,13 @@ int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev, const floa
 int l3d_soft_correspondence_dscores(const float* src_emb_dev, const float* tgt_emb_dev, const float* tgt_xyz_dev,
                                     const float* stats_dev, const float* grad_corr_dev, const float* corr_dev, int B,
                                     int D, int Ns, int Nt, float* ds_dev, float* ds_t_dev, void* stream);
-int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev, int B,
-                  int M, int K, int P, int relu, int w_heads, float* out_dev, void* stream);
-int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, float* stats_dev,
-                        void* stream);
-int l3d_attention_probs_t(const float* q_dev, const float* k_dev, const float* stats_dev, int BH, int D, int Nq,
-                          int Nk, float* probs_t_dev, void* stream);
+int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev,
+                  const float* col_div_dev, int B, int M, int K, int P, int relu, int w_heads, float* out_dev,
+                  void* stream);
+int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, int precise,
+                        float* stats_dev, void* stream);
+int l3d_attention_probs_t(const float* q_dev, const float* k_dev, float* stats_dev, int BH, int D, int Nq, int Nk,
+                          int normalized, float* probs_t_dev, void* stream);
 int l3d_layernorm_cm(const float* x_dev, const float* a2_dev, const float* b2_dev, float eps, int B, int D, int N,
                      float* out_dev, void* stream);
 /* Synchronises the device; returns and clears the pipeline error word of l3d_conv1x1_bn_relu_maxk (0 = ok). */

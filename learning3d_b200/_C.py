@@ -74,9 +74,9 @@ _SIGNATURES = {
     "l3d_conv1x1_bn_relu_maxk": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, ctypes.c_longlong, _I, _P],
     "l3d_edgeconv_status": [],
     "l3d_soft_correspondence_dscores": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
-    "l3d_linear_cm": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
-    "l3d_attention_stats": [_P, _P, _I, _I, _I, _I, _P, _P],
-    "l3d_attention_probs_t": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "l3d_linear_cm": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "l3d_attention_stats": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "l3d_attention_probs_t": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "l3d_layernorm_cm": [_P, _P, _P, _F, _I, _I, _I, _P, _P],
     "l3d_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "l3d_chamfer_backward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <omp.h>
+#include <thread>
 #include <cstdlib>
 #include <mutex>
 
@@ -124,7 +125,10 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
     const char* ev_t = getenv("L3D_HOST_THREADS");
     nthreads = ev_t ? atoi(ev_t) : 4;      // 1 / 2 / 4 / 8 / 16 threads at 8 slices: 253 / 190 / 158 / 159 / 157 us
     if (nthreads < 1) nthreads = 1;
-    if (nthreads > omp_get_max_threads()) nthreads = omp_get_max_threads();
+    // NOT clamped by omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, and the num_threads
+    // clause below is allowed to exceed that default; clamp by the machine instead
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && nthreads > hw) nthreads = hw;
   }
   for (int i = 0; i < nslice; ++i) {
     e = cudaEventSynchronize(ev[i]);

@@ -70,6 +70,7 @@ struct EdgeParams {
   int tiles_per_item, m_blocks, units;
   int relu;
   const float* residual; // optional [B, M, P]: added after the activation (transformer sublayers: x + f(norm(x)))
+  const float* col_div;  // optional [B, P]: every output column p is divided by col_div[b, p] (attention: p.v / row sum)
   int w_heads;           // 0: one weight matrix for every item.  h > 0: item b uses rows (b % h)*M.. of weight batch b / h
 };
 
@@ -197,6 +198,12 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
         for (int e = 0; e < 32; ++e) {
           const float y = fmaf(v[e], s, sf);
           v[e] = p.relu ? fmaxf(y, 0.f) : y;
+        }
+        if (p.col_div) {
+          const float* cd = p.col_div + (size_t)un.b * p.P + un.j0 + ch * 32;      // same address in every lane
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nv) v[e] = __fdividef(v[e], __ldg(cd + e));
         }
         if (!p.h_out) return;
         if (vec) {
@@ -556,7 +563,8 @@ static cudaError_t edge_set_attrs() {
 }
 
 static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float* scale_dev, const float* shift_dev,
-                            const float* residual_dev, int w_heads, int B, int M, int K, int P, int G, int relu,
+                            const float* residual_dev, const float* col_div_dev, int w_heads, int B, int M, int K, int P,
+                            int G, int relu,
                             float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
                             void* stream) {
   if (B < 0 || M < 1 || K < 1 || P < 1 || G < 1) return L3D_ERR_INVALID;
@@ -572,7 +580,7 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
   p.scale = scale_dev; p.shift = shift_dev; p.h_out = h_out_dev; p.pool_out = pool_out_dev;
   p.pool_bstride = (long)pool_bstride; p.pool_coff = pool_coff;
   p.B = B; p.M = M; p.K = K; p.P = P; p.G = G; p.relu = relu;
-  p.residual = residual_dev; p.w_heads = w_heads;
+  p.residual = residual_dev; p.w_heads = w_heads; p.col_div = col_div_dev;
   if (pool_out_dev) {
     p.TS = edge_tile_stride(G);
     p.pool_n = P / G;
@@ -657,8 +665,8 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
                                         float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
                                         void* stream) {
   if (!scale_dev) return L3D_ERR_INVALID;
-  return edge_gemm_launch(wt_dev, x_dev, scale_dev, shift_dev, nullptr, 0, B, M, K, P, G, relu, h_out_dev, pool_out_dev,
-                          pool_bstride, pool_coff, stream);
+  return edge_gemm_launch(wt_dev, x_dev, scale_dev, shift_dev, nullptr, nullptr, 0, B, M, K, P, G, relu, h_out_dev,
+                          pool_out_dev, pool_bstride, pool_coff, stream);
 }
 
 // Channel-major linear layer  out[b, m, p] = act(sum_k wt[.., k, m] x[b, k, p] + bias[m]) (+ residual[b, m, p])
@@ -666,12 +674,15 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
 // w_heads = 0: wt_dev [K, M] shared by all items.  w_heads = h > 0 ("one head per item", the P.V product of
 // attention): x_dev has B = batch*h items, wt_dev is [batch, K, h*M] and item b uses columns (b % h)*M.. of weight
 // batch b / h; M must be a multiple of 128.
+// col_div_dev (optional, [B, P]): every output column is divided by it — the attention row sums when x_dev holds
+// unnormalised probabilities.
 extern "C" int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev,
-                             int B, int M, int K, int P, int relu, int w_heads, float* out_dev, void* stream) {
+                             const float* col_div_dev, int B, int M, int K, int P, int relu, int w_heads,
+                             float* out_dev, void* stream) {
   if (!out_dev) return L3D_ERR_INVALID;
   if ((M * w_heads) & 3) return L3D_ERR_UNSUPPORTED;
-  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, residual_dev, w_heads, B, M, K, P, 1, relu, out_dev, nullptr,
-                          0, 0, stream);
+  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, residual_dev, col_div_dev, w_heads, B, M, K, P, 1, relu,
+                          out_dev, nullptr, 0, 0, stream);
 }
 
 // Synchronises the device and returns (then clears) the pipeline error word of l3d_conv1x1_bn_relu_maxk:

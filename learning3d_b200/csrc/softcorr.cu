@@ -81,6 +81,10 @@ struct SoftCorrParams {
   // the TRANSPOSED probabilities P^T [B, Nt, Ns] (the B operand of the P.V GEMM, l3d_conv1x1_bn_relu_maxk)
   float* stats;           // [B, Ns, 2]: (running max in log2 units, sum of 2^(s - max))
   float* probs_t;         // [B, Nt, Ns]
+  int single_pass;        // EPI_STATS: one TF32 MMA per k-step (hi.hi only): the row max to ~1e-3 relative is all the
+                          // probability pass needs as its exponent reference
+  int probs_unnormalized; // EPI_PROBS_T: write 2^(s c - m_i) WITHOUT the 1/l_i factor and store the exact row sums
+                          // l_i = sum_j 2^(s c - m_i) into stats[.., 1] (the p.v GEMM divides its columns by them)
   // EPI_DS (backward of the soft correspondences): dS[i,j] = P[i,j] (g_i . tgt_j - g_i . corr_i) / sqrt(D)
   const float* grad_corr; // [B, 3, Ns]  dL/d src_corr
   const float* corr;      // [B, 3, Ns]  src_corr of the forward
@@ -374,8 +378,13 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
           if (i < p.Ns) {
             float* dst = p.probs_t + ((size_t)b * p.Nt + j0 + ch * 32) * p.Ns + i;
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (ch * 32 + e < nvalid) dst[(size_t)e * p.Ns] = __fmul_rn(ex2_approx(fmaf(v[e], c, -pm)), pinv);
+            for (int e = 0; e < 32; ++e) {
+              if (ch * 32 + e < nvalid) {
+                const float pe = ex2_approx(fmaf(v[e], c, -pm));
+                l = __fadd_rn(l, pe);
+                dst[(size_t)e * p.Ns] = p.probs_unnormalized ? pe : __fmul_rn(pe, pinv);
+              }
+            }
           }
           continue;
         }
@@ -433,6 +442,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       p.stats[((size_t)b * p.Ns + i) * 2] = ok ? m : qn;
       p.stats[((size_t)b * p.Ns + i) * 2 + 1] = ok ? l : qn;
     }
+    if (EPI == EPI_PROBS_T && ok && p.probs_unnormalized && i < p.Ns) p.stats[((size_t)b * p.Ns + i) * 2 + 1] = l;
     if (EPI == EPI_PROBS_T && !ok && i < p.Ns) {
       for (int j = 0; j < p.Nt; ++j) p.probs_t[((size_t)b * p.Nt + j) * p.Ns + i] = __int_as_float(0x7fc00000);
     }
@@ -459,7 +469,7 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
         if (!mbar_wait_bounded(&sh->tma_full[s], n & 1u)) { ok = false; break; }
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {
+        for (int op = 0; op < (p.single_pass ? 0 : 2); ++op) {
           const uint32_t hi = st + (op ? 2 * A_TILE : 0), lo = hi + (op ? B_TILE : A_TILE);
 #pragma unroll
           for (int q = 0; q < (op ? B_TILE : A_TILE) / 16 / SC_PROD_THREADS; ++q) {
@@ -534,7 +544,10 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
           for (int k = 0; k < SC_BK / SC_UK; ++k) {
             // K-major: +32 bytes inside the 128 B swizzle row; MN-major: next 8-channel group (+1024 B)
             const uint64_t adv = (uint64_t)((USE_TMA ? k * 1024 : k * SC_UK * 4) >> 4);
-            if (PAIR) {
+            if (p.single_pass) {
+              if (PAIR) tc_mma_tf32_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+              else tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            } else if (PAIR) {
               tc_mma_tf32_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
               tc_mma_tf32_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
               tc_mma_tf32_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
@@ -682,7 +695,8 @@ static int sc_launch(SoftCorrParams p, void* stream) {
   }
   const long slots = pair ? sm_count / 2 : sm_count;   // 1 CTA per SM; a pair needs both SMs of a TPC
   int jsplit = 1;
-  if (EPI != EPI_STATS && EPI != EPI_DS && g_softcorr_split >= 0 && tiles > 1 && units * 2 <= slots) {
+  if (EPI != EPI_STATS && EPI != EPI_DS && !(EPI == EPI_PROBS_T && p.probs_unnormalized) && g_softcorr_split >= 0 &&
+      tiles > 1 && units * 2 <= slots) {
     jsplit = (int)((slots + units - 1) / units);
     if (g_softcorr_split > 0) jsplit = g_softcorr_split;
     if (jsplit > tiles) jsplit = tiles;
@@ -864,7 +878,9 @@ extern "C" int l3d_knn_features(const float* x_dev, int B, int C, int N, int k, 
 // ---- attention (utils/transformer.py:17-23): softmax(q k^T / sqrt(d_k)) in two passes over the tcgen05 score
 // pipeline; the probabilities leave the kernel transposed, ready to be the activation operand of the P.V GEMM.
 // q_dev [BH, D, Nq], k_dev [BH, D, Nk] (channel-major per batch x head) -> stats_dev [BH, Nq, 2]
-extern "C" int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk,
+// precise = 0: the row max from ONE TF32 pass (the exponent reference only has to be close to the true max; the
+// row sum slot is then meaningless and is rewritten by l3d_attention_probs_t(normalized = 0) with the exact sums)
+extern "C" int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, int precise,
                                    float* stats_dev, void* stream) {
   if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
   if (BH == 0 || Nq == 0) return L3D_OK;
@@ -873,18 +889,20 @@ extern "C" int l3d_attention_stats(const float* q_dev, const float* k_dev, int B
   memset(&p, 0, sizeof(p));
   p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = stats_dev;
   p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
+  p.single_pass = precise ? 0 : 1;
   return sc_launch<EPI_STATS>(p, stream);
 }
 // ... + stats_dev -> probs_t_dev [BH, Nk, Nq] = softmax(q^T k / sqrt(D), over k) transposed
-extern "C" int l3d_attention_probs_t(const float* q_dev, const float* k_dev, const float* stats_dev, int BH, int D,
-                                     int Nq, int Nk, float* probs_t_dev, void* stream) {
+extern "C" int l3d_attention_probs_t(const float* q_dev, const float* k_dev, float* stats_dev, int BH, int D, int Nq,
+                                     int Nk, int normalized, float* probs_t_dev, void* stream) {
   if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
   if (BH == 0 || Nq == 0) return L3D_OK;
   if (!q_dev || !k_dev || !stats_dev || !probs_t_dev) return L3D_ERR_INVALID;
   SoftCorrParams p;
   memset(&p, 0, sizeof(p));
-  p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = const_cast<float*>(stats_dev); p.probs_t = probs_t_dev;
+  p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = stats_dev; p.probs_t = probs_t_dev;
   p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
+  p.probs_unnormalized = normalized ? 0 : 1;
   return sc_launch<EPI_PROBS_T>(p, stream);
 }
 

@@ -87,7 +87,8 @@ class _SoftCorr(torch.autograd.Function):
         with _C.on_device(dev):
             st = _C.stream()
             stats = torch.empty((B, Ns, 2), dtype=torch.float32, device=dev)
-            _C.check(lib.l3d_attention_stats(_C.ptr(src_emb), _C.ptr(tgt_emb), B, D, Ns, Nt, _C.ptr(stats), st), "softcorr stats")
+            _C.check(lib.l3d_attention_stats(_C.ptr(src_emb), _C.ptr(tgt_emb), B, D, Ns, Nt, 1, _C.ptr(stats), st),
+                     "softcorr stats")
             need_s, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             ds = torch.empty((B, Ns, Nt), dtype=torch.float32, device=dev) if need_t else None
             ds_t = torch.empty((B, Nt, Ns), dtype=torch.float32, device=dev) if need_s else None
@@ -98,13 +99,13 @@ class _SoftCorr(torch.autograd.Function):
             if need_s:          # d src_emb [B,D,Ns] = tgt_emb [D x Nt] . dS^T [Nt x Ns]
                 wt = tgt_emb.transpose(1, 2).contiguous()
                 g_src = torch.empty_like(src_emb)
-                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds_t), _C.ptr(None), _C.ptr(None), B, D, Nt, Ns, 0, 1,
-                                           _C.ptr(g_src), st), "softcorr d src_emb")
+                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds_t), _C.ptr(None), _C.ptr(None), _C.ptr(None), B, D, Nt, Ns,
+                                           0, 1, _C.ptr(g_src), st), "softcorr d src_emb")
             if need_t:          # d tgt_emb [B,D,Nt] = src_emb [D x Ns] . dS [Ns x Nt]
                 wt = src_emb.transpose(1, 2).contiguous()
                 g_tgt = torch.empty_like(tgt_emb)
-                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds), _C.ptr(None), _C.ptr(None), B, D, Ns, Nt, 0, 1,
-                                           _C.ptr(g_tgt), st), "softcorr d tgt_emb")
+                _C.check(lib.l3d_linear_cm(_C.ptr(wt), _C.ptr(ds), _C.ptr(None), _C.ptr(None), _C.ptr(None), B, D, Ns, Nt,
+                                           0, 1, _C.ptr(g_tgt), st), "softcorr d tgt_emb")
         return g_src, g_tgt, None
 
 

@@ -33,8 +33,8 @@ def linear_cm(x, lin, relu=False, residual=None):
     B, K, N = x.shape
     M = wt.shape[1]
     out = torch.empty((B, M, N), dtype=torch.float32, device=x.device)
-    _C.check(_C.lib().l3d_linear_cm(_C.ptr(wt), _C.ptr(x), _C.ptr(bias), _C.ptr(residual), B, M, K, N, 1 if relu else 0,
-                                    0, _C.ptr(out), _C.stream()), "linear")
+    _C.check(_C.lib().l3d_linear_cm(_C.ptr(wt), _C.ptr(x), _C.ptr(bias), _C.ptr(residual), _C.ptr(None), B, M, K, N,
+                                    1 if relu else 0, 0, _C.ptr(out), _C.stream()), "linear")
     return out
 
 
@@ -58,14 +58,17 @@ def attention_cm(attn, xq, xkv, residual):
     v = linear_cm(xkv, attn.linears[2])
     st = _C.stream()
     stats = torch.empty((B * h, Nq, 2), dtype=torch.float32, device=xq.device)
-    _C.check(lib.l3d_attention_stats(_C.ptr(q), _C.ptr(k), B * h, dk, Nq, Nk, _C.ptr(stats), st), "attention stats")
+    # pass 1: row maxima from ONE TF32 MMA pass (only an exponent reference); pass 2: 3xTF32 scores again,
+    # unnormalised probabilities 2^(s - max) written transposed + the exact row sums
+    _C.check(lib.l3d_attention_stats(_C.ptr(q), _C.ptr(k), B * h, dk, Nq, Nk, 0, _C.ptr(stats), st), "attention stats")
     probs_t = torch.empty((B * h, Nk, Nq), dtype=torch.float32, device=xq.device)
-    _C.check(lib.l3d_attention_probs_t(_C.ptr(q), _C.ptr(k), _C.ptr(stats), B * h, dk, Nq, Nk, _C.ptr(probs_t), st),
+    _C.check(lib.l3d_attention_probs_t(_C.ptr(q), _C.ptr(k), _C.ptr(stats), B * h, dk, Nq, Nk, 0, _C.ptr(probs_t), st),
              "attention probabilities")
+    rowsum = stats[:, :, 1].contiguous()                        # [B*h, Nq]
     vt = v.transpose(1, 2).contiguous()                       # [B, Nk, h*d_k]: v^T, heads side by side
     ctx = torch.empty((B, d, Nq), dtype=torch.float32, device=xq.device)      # = [B*h, d_k, Nq]
-    _C.check(lib.l3d_linear_cm(_C.ptr(vt), _C.ptr(probs_t), _C.ptr(None), _C.ptr(None), B * h, dk, Nk, Nq, 0, h,
-                               _C.ptr(ctx), st), "attention p.v")
+    _C.check(lib.l3d_linear_cm(_C.ptr(vt), _C.ptr(probs_t), _C.ptr(None), _C.ptr(None), _C.ptr(rowsum), B * h, dk, Nk,
+                               Nq, 0, h, _C.ptr(ctx), st), "attention p.v")
     return linear_cm(ctx, attn.linears[3], residual=residual)
 
 

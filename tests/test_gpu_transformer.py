@@ -95,3 +95,31 @@ def test_transformer_forward_fused_vs_torch_path():
     a, b = net(src, tgt)
     (a.mean() + b.mean()).backward()
     assert src.grad is not None
+
+
+def test_attention_protocols_agree():
+    """precise stats + normalised probabilities vs the fast protocol (one-pass TF32 max, unnormalised probabilities,
+    row sums divided out by the p.v GEMM): same context to fp32-GEMM accuracy."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    torch.manual_seed(12)
+    BH, D, Nq, Nk = 8, 128, 260, 512
+    q = torch.randn(BH, D, Nq, device=DEV); k = torch.randn(BH, D, Nk, device=DEV) * 2
+    vt = torch.randn(BH // 4, Nk, 4 * 128, device=DEV)
+    st = _C.stream()
+    outs = []
+    for precise, normalized in ((1, 1), (0, 0)):
+        stats = torch.empty(BH, Nq, 2, device=DEV); pt = torch.empty(BH, Nk, Nq, device=DEV)
+        _C.check(lib.l3d_attention_stats(_C.ptr(q), _C.ptr(k), BH, D, Nq, Nk, precise, _C.ptr(stats), st))
+        _C.check(lib.l3d_attention_probs_t(_C.ptr(q), _C.ptr(k), _C.ptr(stats), BH, D, Nq, Nk, normalized, _C.ptr(pt), st))
+        div = None if normalized else stats[:, :, 1].contiguous()
+        ctx = torch.empty(BH, 128, Nq, device=DEV)
+        _C.check(lib.l3d_linear_cm(_C.ptr(vt), _C.ptr(pt), _C.ptr(None), _C.ptr(None), _C.ptr(div), BH, 128, Nk, Nq, 0, 4,
+                                   _C.ptr(ctx), st))
+        outs.append(ctx)
+    p = torch.softmax(torch.einsum("bdq,bdk->bqk", q.double(), k.double()) / math.sqrt(D), dim=-1)
+    v = vt.double().view(BH // 4, Nk, 4, 128).permute(0, 2, 3, 1).reshape(BH, 128, Nk)           # [BH, d_v, Nk]
+    want = torch.einsum("bdk,bqk->bdq", v, p)
+    for o in outs:
+        assert (o.double() - want).abs().max().item() < 1e-5
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-5
