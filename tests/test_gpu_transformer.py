@@ -120,6 +120,9 @@ def test_attention_protocols_agree():
     p = torch.softmax(torch.einsum("bdq,bdk->bqk", q.double(), k.double()) / math.sqrt(D), dim=-1)
     v = vt.double().view(BH // 4, Nk, 4, 128).permute(0, 2, 3, 1).reshape(BH, 128, Nk)           # [BH, d_v, Nk]
     want = torch.einsum("bdk,bqk->bdq", v, p)
-    for o in outs:
-        assert (o.double() - want).abs().max().item() < 1e-5
-    assert (outs[0] - outs[1]).abs().max().item() < 1e-5
+    # peaky softmax here (scores ~ N(0, 4)): the fp32-GEMM error of a score (<= 4e-6 * sum|q||k| ~ 6e-4) moves a
+    # probability by up to ~8e-5 relative; both protocols sit at 1-3e-5 absolute on outputs of magnitude ~3
+    errs = [(o.double() - want).abs().max().item() for o in outs]
+    print("attention protocols: precise %.3g, fast %.3g, between %.3g" % (errs[0], errs[1], (outs[0] - outs[1]).abs().max().item()))
+    assert max(errs) < 6e-5
+    assert (outs[0] - outs[1]).abs().max().item() < 6e-5
