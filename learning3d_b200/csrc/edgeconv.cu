@@ -385,24 +385,27 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
     // ------------------------------------------------ TMA issuer: 4 weight boxes + 8 (4 in a pair) activation boxes
     bool ok = true;
     int it = 0;
-    // The ring holds one to two tiles of activations (96 KB of loaded bytes per SM): at HBM latency under load that is
-    // ~2.5 TB/s over the GPU (measured on layers 2-3, profiles/r02).  The activation boxes EC_PF stages beyond the
-    // ring are therefore prefetched into L2 (UTMAPF.L2: no shared memory, no barrier), so the ring's own loads hit L2.
-    constexpr int EC_PF = 12;                                   // pipeline stages (16-channel slabs) of look-ahead
+    // Tried and rejected (profiles/r02/README.md): prefetching the activation boxes 12 stages beyond the ring into L2
+    // (UTMAPF.L2).  The prefetches queue in the same TMA pipe ahead of the ring's own loads and made every layer
+    // slower (layer 2: 108 -> 183 us, p.v: 188 -> 310 us).  -DL3D_EC_PREFETCH=<stages> rebuilds the experiment.
+#ifndef L3D_EC_PREFETCH
+#define L3D_EC_PREFETCH 0
+#endif
+    constexpr int EC_PF = L3D_EC_PREFETCH;                      // pipeline stages (16-channel slabs) of look-ahead
     auto prefetch_stage = [&](int j) {                          // j = index in this CTA's (tile, k-block) sequence
-      if (j >= total) return;
+      if (EC_PF == 0 || j >= total) return;
       const int t = j / num_kb, kb = j - t * num_kb;
       const EdgeUnit pu = edge_unit(p, cluster_id + t * n_clusters, CTAS, crank);
 #pragma unroll
       for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
         tma_prefetch_3d(&tmap_x, pu.j0 + (int)crank * Cfg::BN_LOCAL + 32 * q, kb * EC_BK, pu.b);
     };
-    if (lane == 0)
+    if (EC_PF > 0 && lane == 0)
       for (int j = STAGES; j < STAGES + EC_PF; ++j) prefetch_stage(j);
     for (int t = 0; t < my_tiles && ok; ++t) {
       const EdgeUnit un = edge_unit(p, cluster_id + t * n_clusters, CTAS, crank);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        if (lane == 0) prefetch_stage(it + STAGES + EC_PF);
+        if (EC_PF > 0 && lane == 0) prefetch_stage(it + STAGES + EC_PF);
         const int s = it % STAGES;
         const uint32_t n = (uint32_t)(it / STAGES);
         if (!mbar_wait_bounded(&sh->empty[s], (n & 1u) ^ 1u)) { ok = false; break; }

@@ -39,7 +39,13 @@ class DCP(nn.Module):
         self.head = SVDHead(self.emb_nn.emb_dims)
 
     def forward(self, template, source):
-        src_f, tpl_f = self.emb_nn(source), self.emb_nn(template)
+        if not self.training and source.shape == template.shape:
+            # eval: one 2B-cloud pass through the embedding network (BatchNorm uses running statistics, so this
+            # equals the two separate calls of models/dcp.py:31-32) — half the launches, fuller waves
+            both = self.emb_nn(torch.cat([source, template], 0))
+            src_f, tpl_f = both[:source.shape[0]].contiguous(), both[source.shape[0]:].contiguous()
+        else:
+            src_f, tpl_f = self.emb_nn(source), self.emb_nn(template)
         src_p, tpl_p = self.pointer(src_f, tpl_f)
         src_f, tpl_f = src_f + src_p, tpl_f + tpl_p
         rot_ab, trans_ab = self.head(src_f, tpl_f, source, template)
