@@ -32,7 +32,8 @@ extern "C" {
 #define L3D_ERR_INVALID (-1)
 #define L3D_ERR_UNSUPPORTED (-2)
 
-/* Largest candidate cloud the selection kernels keep resident in shared memory. */
+/* Largest candidate cloud the selection kernels keep resident in shared memory (the fast path).  Larger clouds are
+ * streamed through a shared-memory tile with the same arithmetic and ordering (any N; k <= 2048 there). */
 #define L3D_KNN_MAX_N 8192
 
 /* ---- library ------------------------------------------------------------------- */
@@ -56,7 +57,8 @@ void l3d_debug_force_slow_path(int on);
  *           pd = ((-|x_j|^2) + 2 x_i.x_j) - |x_i|^2   (model_common_utils.py:5-7)
  * Arithmetic: x_i.x_j = fma(z,z', fma(y,y', x*x')) — the K=3 GEMM accumulation order of
  * torch.matmul (verified against MKL, oracle/README.md); ties -> lower index first.
- * Requires 1 <= k <= N <= L3D_KNN_MAX_N.
+ * Requires 1 <= k <= N.  N <= L3D_KNN_MAX_N runs the resident kernel, larger clouds the streamed selection
+ * (same results, k <= 2048).
  */
 int l3d_knn_expansion(const float* x_dev, int B, int N, int k, int64_t* idx_dev,
                       float* val_dev, void* stream);
@@ -211,7 +213,8 @@ int l3d_pn2_gather_points_grad(int b, int c, int n, int npoints, const float* gr
 /* furthest_point_sampling_wrapper(b,n,m,points,temp,idx)  (sampling_gpu.cu:93-246;
  * pointnet2_utils.py:28): temp_dev [b,n] must hold 1e10 on entry (caller-filled, as in the
  * reference) and holds the final min-distances on return; idxs_dev [b,m] int32, idxs[:,0] = 0.
- * Index-exact including the reference's tie rule.  n <= 8192. */
+ * Index-exact including the reference's tie rule.  n <= 8192 runs with the
+ * cloud and the minima in registers / shared memory; larger clouds keep the minima in temp_dev. */
 int l3d_pn2_furthest_point_sampling(int b, int n, int m, const float* dataset_dev, float* temp_dev,
                                     int32_t* idxs_dev, void* stream);
 /* three_interpolate_wrapper(b,c,m,n,points,idx,weight,out)  (interpolate_gpu.cu:149-169;
@@ -239,7 +242,8 @@ int l3d_query_ball_point(const float* xyz_dev, const float* new_xyz_dev, int B, 
 /*
  * farthest_point_sample() (model_common_utils.py:58-82, pointconv_util.py:60-83,
  * ppfnet_util.py:71-93): start_dev optional [B] int64 first indices (NULL = start at 0, the
- * pointconv / start_with_first_point variant); centroids_dev [B,npoint] int64.  N <= 8192.
+ * pointconv / start_with_first_point variant); centroids_dev [B,npoint] int64.  N > 8192 takes a
+ * stream-ordered scratch array (cudaMallocAsync) for the running minima.
  */
 int l3d_farthest_point_sample(const float* xyz_dev, int B, int N, int npoint,
                               const int64_t* start_dev, int64_t* centroids_dev, void* stream);

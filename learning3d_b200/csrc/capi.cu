@@ -59,7 +59,7 @@ extern "C" uint64_t l3d_launch_count(void) {
 
 // knn() from HOST buffers.  The call is PCIe-bound on its OUTPUT: 8*k bytes of int64 indices return per 12 bytes of
 // input (5.2 MB per C2 batch, ~100 us of D2H at the ~50 GB/s a pinned copy reaches), three times the kernel.  Every
-// index is < N <= 8192, so the device writes uint16, 2 bytes per index cross the bus (1.3 MB) into an internal pinned
+// index is < N (N <= 65536 on this path; larger clouds return int64 directly), so the device writes uint16, 2 bytes per index cross the bus (1.3 MB) into an internal pinned
 // staging buffer, and the host widens them to the caller's int64 array with a few OpenMP threads while the next
 // slice is still in flight.  The batch is cut into (by default two) slices on two streams (clouds are independent);
 // more slices overlap better on paper but every slice costs four driver calls, and those ~4 us each are what the
@@ -70,9 +70,22 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   std::lock_guard<std::mutex> lock(l3d::g_host.mu);
   const size_t in_bytes = (size_t)B * 3 * N * sizeof(float);
   const size_t n_idx = (size_t)B * N * k;
+  cudaError_t e;
+  if (N > 65536) {
+    // an index no longer fits the 16-bit wire format: int64 indices straight into the caller's buffer, one launch
+    int rc64 = l3d::g_host.ensure(in_bytes, n_idx * sizeof(int64_t));
+    if (rc64) return rc64;
+    cudaStream_t s = l3d::g_host.stream;
+    e = cudaMemcpyAsync(l3d::g_host.in, x_host, in_bytes, cudaMemcpyHostToDevice, s);
+    if (e) return (int)e;
+    rc64 = l3d_knn_expansion((const float*)l3d::g_host.in, B, N, k, (int64_t*)l3d::g_host.out, nullptr, (void*)s);
+    if (rc64) return rc64;
+    e = cudaMemcpyAsync(idx_host, l3d::g_host.out, n_idx * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e) return (int)e;
+    return (int)cudaStreamSynchronize(s);
+  }
   int rc = l3d::g_host.ensure(in_bytes, n_idx * sizeof(unsigned short));
   if (rc) return rc;
-  cudaError_t e;
   // grow-only pinned staging buffer for the narrow indices
   static unsigned short* stage = nullptr;
   static size_t stage_cap = 0;

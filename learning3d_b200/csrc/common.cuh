@@ -202,6 +202,11 @@ __device__ __forceinline__ unsigned long long pack_pair(float key, uint32_t idx)
   // key + 0.0f folds -0.0 into +0.0 so that equal keys always produce equal high words
   return ((unsigned long long)f32_order(key + 0.0f) << 32) | (unsigned long long)(~idx);
 }
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(L3D_FULL_MASK, (uint32_t)v, src);
+  const uint32_t hi = __shfl_sync(L3D_FULL_MASK, (uint32_t)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
   const uint32_t lo = __shfl_xor_sync(L3D_FULL_MASK, (uint32_t)v, m);
   const uint32_t hi = __shfl_xor_sync(L3D_FULL_MASK, (uint32_t)(v >> 32), m);

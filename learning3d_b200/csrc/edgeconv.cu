@@ -71,6 +71,7 @@ struct EdgeParams {
   int relu;
   const float* residual; // optional [B, M, P]: added after the activation (transformer sublayers: x + f(norm(x)))
   const float* col_div;  // optional [B, P]: every output column p is divided by col_div[b, p] (attention: p.v / row sum)
+  int w4, x4;            // chunked 4-D tensor maps: weights; activations (bit 0: tiles at 32-position multiples, bit 1: +16)
   int w_heads;           // 0: one weight matrix for every item.  h > 0: item b uses rows (b % h)*M.. of weight batch b / h
 };
 
@@ -104,10 +105,13 @@ __device__ __forceinline__ EdgeUnit edge_unit(const EdgeParams& p, int u, int ct
 }
 
 // GT: compile-time pooling group size for the epilogue's fast path (20 = DGCNN's k; 1 = the generic path only)
+int tma3_boxes_forced();   // softcorr.cu: testing hook (l3d_debug_soft_correspondence_force_generic(3))
+
 template <int CTAS, int GT>
 __global__ void __launch_bounds__(EC_THREADS, 1)
 edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_x) {
+                 const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x4a,
+                 const __grid_constant__ CUtensorMap tmap_x4b) {
   using Cfg = EdgeCfg<CTAS>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE, A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE;
   constexpr bool PAIR = (CTAS == 2);
@@ -199,7 +203,7 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
           const float y = fmaf(v[e], s, sf);
           v[e] = p.relu ? fmaxf(y, 0.f) : y;
         }
-        if (p.col_div) {
+        if (GT == 1 && p.col_div) {          // linear layers only: keeps the pooled kernels' epilogue free of it
           const float* cd = p.col_div + (size_t)un.b * p.P + un.j0 + ch * 32;      // same address in every lane
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -221,7 +225,7 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
             const int cr = cbase + r + rr;
             if (cr < p.M && cq * 4 < nv) {
               const size_t off = ((size_t)un.b * p.M + cr) * p.P + un.j0 + ch * 32 + cq * 4;
-              if (p.residual) {
+              if (GT == 1 && p.residual) {
                 const float4 rz = __ldg(reinterpret_cast<const float4*>(p.residual + off));
                 o.x += rz.x; o.y += rz.y; o.z += rz.z; o.w += rz.w;
               }
@@ -233,7 +237,7 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
           const size_t off = ((size_t)un.b * p.M + c) * p.P + un.j0 + ch * 32;
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (e < nv) p.h_out[off + e] = p.residual ? v[e] + __ldg(p.residual + off + e) : v[e];
+            if (e < nv) p.h_out[off + e] = (GT == 1 && p.residual) ? v[e] + __ldg(p.residual + off + e) : v[e];
         }
       };
       auto release = [&]() {
@@ -271,9 +275,11 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
         // generic: run-time group size and / or a short last tile
         float gm = -INFINITY;
         int cnt = 0, gi = 0;
-        float pl[EC_MAX_GROUPS];
+        // a kernel with a compile-time group size only comes here for a short last tile: fewer than EC_BN / GT groups
+        constexpr int PLN = GT > 1 ? EC_BN / GT : EC_MAX_GROUPS;
+        float pl[PLN];
 #pragma unroll
-        for (int g = 0; g < EC_MAX_GROUPS; ++g) pl[g] = 0.f;
+        for (int g = 0; g < PLN; ++g) pl[g] = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < EC_BN / 32; ++ch) {
           if (ch * 32 >= nvalid) break;
@@ -287,7 +293,7 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
                 gm = fmaxf(gm, v[e]);
                 if (++cnt == p.G) {
 #pragma unroll
-                  for (int g = 0; g < EC_MAX_GROUPS; ++g) if (g == gi) pl[g] = gm;
+                  for (int g = 0; g < PLN; ++g) if (g == gi) pl[g] = gm;
                   ++gi; gm = -INFINITY; cnt = 0;
                 }
               }
@@ -297,7 +303,7 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
         release();
         if (pdst && vrow) {
 #pragma unroll
-          for (int g = 0; g < EC_MAX_GROUPS; ++g) if (g < gi) pdst[g] = pl[g];
+          for (int g = 0; g < PLN; ++g) if (g < gi) pdst[g] = pl[g];
         }
       }
     }
@@ -413,13 +419,26 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
           const uint32_t st = tiles_s + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&sh->tma_full[s], A_TILE + B_TILE);
           const int wm0 = un.m0 + (p.w_heads ? (un.b % p.w_heads) * p.M : 0), wb = p.w_heads ? un.b / p.w_heads : 0;
+          // chunked 4-D maps (tc05.cuh: make_dn_tmap4): a whole operand tile per instruction.  The activation tile
+          // starts at a multiple of 32 positions (map a) or 16 past one (map b, base shifted by 16 floats: k = 20 tiles
+          // advance by 240); a shifted tile that would run past the row takes the 32-point boxes, which zero-fill.
+          if (p.w4) {
+            tma_load_4d(st, &tmap_w, 0, kb * EC_BK, wm0 / 32, wb, &sh->tma_full[s]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < SC_BM / 32; ++q)
-            tma_load_3d(st + q * Cfg::ATOM, &tmap_w, wm0 + 32 * q, kb * EC_BK, wb, &sh->tma_full[s]);
+            for (int q = 0; q < SC_BM / 32; ++q)
+              tma_load_3d(st + q * Cfg::ATOM, &tmap_w, wm0 + 32 * q, kb * EC_BK, wb, &sh->tma_full[s]);
+          }
+          const int jl = un.j0 + (int)crank * Cfg::BN_LOCAL;
+          if ((p.x4 & 1) && (jl & 31) == 0) {
+            tma_load_4d(st + 2 * A_TILE, &tmap_x4a, 0, kb * EC_BK, jl / 32, un.b, &sh->tma_full[s]);
+          } else if ((p.x4 & 2) && (jl & 31) == 16 && jl + Cfg::BN_LOCAL <= p.P) {
+            tma_load_4d(st + 2 * A_TILE, &tmap_x4b, 0, kb * EC_BK, jl / 32, un.b, &sh->tma_full[s]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
-            tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_x, un.j0 + (int)crank * Cfg::BN_LOCAL + 32 * q, kb * EC_BK,
-                        un.b, &sh->tma_full[s]);
+            for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
+              tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_x, jl + 32 * q, kb * EC_BK, un.b, &sh->tma_full[s]);
+          }
         }
         __syncwarp();
       }
@@ -635,9 +654,35 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
   // weights: [K, M] shared by every item, or (w_heads > 0) [B / w_heads, K, w_heads * M] with one head per item
   const bool wok = w_heads ? make_dn_tmap(&mw, wt_dev, B / w_heads, K, w_heads * M, EC_BK) : make_dn_tmap(&mw, wt_dev, 1, K, M, EC_BK);
   if (!wok || !make_dn_tmap(&mx, x_dev, B, K, P, EC_BK)) return L3D_ERR_UNSUPPORTED;
+  CUtensorMap mx4a, mx4b;
+  memset(&mx4a, 0, sizeof(mx4a)); memset(&mx4b, 0, sizeof(mx4b));
+  if (!tma3_boxes_forced()) {
+    const int xchunks = (pair ? EdgeCfg<2>::BN_LOCAL : EdgeCfg<1>::BN_LOCAL) / 32;
+    CUtensorMap mw4;
+    const bool w4 = w_heads ? make_dn_tmap4(&mw4, wt_dev, B / w_heads, K, w_heads * M, EC_BK, SC_BM / 32)
+                            : make_dn_tmap4(&mw4, wt_dev, 1, K, M, EC_BK, SC_BM / 32);
+    if (w4) { mw = mw4; p.w4 = 1; }
+    const int step = p.TS & 31;                                  // tile starts modulo 32: always 0, or alternating 0 / 16
+    if ((step == 0 || step == 16) && (P & 31) == 0) {
+      if (make_dn_tmap4(&mx4a, x_dev, B, K, P, EC_BK, xchunks)) p.x4 |= 1;
+      // the +16 view: same strides from a base 16 floats in; only chunks that lie wholly inside a row are declared
+      if (step == 16 && P >= 64) {
+        EncodeTiledFn fn = encode_tiled_fn();
+        cuuint64_t dims[4] = {32, (cuuint64_t)K, (cuuint64_t)((P - 16) / 32), (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)P * 4, 128, (cuuint64_t)P * (cuuint64_t)K * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)EC_BK, (cuuint32_t)xchunks, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (fn && fn(&mx4b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(x_dev + 16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          p.x4 |= 2;
+      }
+    }
+  }
 
   const int sms = edge_sm_count(dev);
-  const int gt = (pool_out_dev != nullptr && (G == 20 || G == 16 || G == 8 || G == 64)) ? G : 1;
+  // (the compile-time-G kernels carry no residual / column-divide code)
+  const int gt = (pool_out_dev != nullptr && !residual_dev && !col_div_dev && (G == 20 || G == 16 || G == 8 || G == 64)) ? G : 1;
   if (pair) {
     long clusters = sms / 2;
     if (clusters > units) clusters = units;
@@ -653,11 +698,11 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
     // group sizes with a compile-time epilogue (static group boundaries): DGCNN's k = 20, FlowNet3D's 8 / 16 / 64
     cudaError_t le;
     switch (gt) {
-      case 20: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 20>, p, mw, mx); break;
-      case 16: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 16>, p, mw, mx); break;
-      case 8: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 8>, p, mw, mx); break;
-      case 64: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 64>, p, mw, mx); break;
-      default: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 1>, p, mw, mx);
+      case 20: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 20>, p, mw, mx, mx4a, mx4b); break;
+      case 16: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 16>, p, mw, mx, mx4a, mx4b); break;
+      case 8: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 8>, p, mw, mx, mx4a, mx4b); break;
+      case 64: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 64>, p, mw, mx, mx4a, mx4b); break;
+      default: le = cudaLaunchKernelEx(&cfg, edge_gemm_kernel<2, 1>, p, mw, mx, mx4a, mx4b);
     }
     if (le != cudaSuccess) return (int)le;
   } else {
@@ -666,11 +711,11 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
     const size_t sm1 = edge_smem_bytes<1>();
     cudaStream_t st = (cudaStream_t)stream;
     switch (gt) {
-      case 20: edge_gemm_kernel<1, 20><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
-      case 16: edge_gemm_kernel<1, 16><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
-      case 8: edge_gemm_kernel<1, 8><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
-      case 64: edge_gemm_kernel<1, 64><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx); break;
-      default: edge_gemm_kernel<1, 1><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx);
+      case 20: edge_gemm_kernel<1, 20><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx, mx4a, mx4b); break;
+      case 16: edge_gemm_kernel<1, 16><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx, mx4a, mx4b); break;
+      case 8: edge_gemm_kernel<1, 8><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx, mx4a, mx4b); break;
+      case 64: edge_gemm_kernel<1, 64><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx, mx4a, mx4b); break;
+      default: edge_gemm_kernel<1, 1><<<(unsigned)grid, EC_THREADS, sm1, st>>>(p, mw, mx, mx4a, mx4b);
     }
   }
   count_launch();

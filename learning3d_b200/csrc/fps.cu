@@ -149,10 +149,69 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const FpsParams p) {
   }
 }
 
+// Clouds beyond the register-resident kernel (N > 16 * FPS_THREADS = 8192; the reference kernel and the torch loops
+// have no size limit): same rounds, same distance forms and tie keys, but the running minimum lives in the caller's
+// `temp` array (or a stream-ordered scratch for the torch variants) and the coordinates are re-read through L1/L2
+// every round.  Each thread owns the same elements k = tid, tid + 1024, ... in every round, so no two threads ever
+// touch the same temp[k].
+constexpr int FPS_BIG_THREADS = 1024;
+
+__global__ void __launch_bounds__(FPS_BIG_THREADS) fps_stream_kernel(const FpsParams p, float* scratch) {
+  __shared__ uint2 s_r[2][FPS_BIG_THREADS / 32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, M = p.M;
+  const float* xyz = p.xyz + (size_t)b * N * 3;
+  float* temp = (p.temp ? p.temp : scratch) + (size_t)b * N;
+  if (!p.temp)
+    for (int k = tid; k < N; k += FPS_BIG_THREADS) temp[k] = 1e10f;   // own elements only: no barrier needed
+
+  int old = p.start ? (int)p.start[b] : 0;
+  if (tid == 0) {
+    if (p.idx64) reinterpret_cast<long long*>(p.out)[(size_t)b * M] = old;
+    else reinterpret_cast<int*>(p.out)[(size_t)b * M] = old;
+  }
+  for (int j = 1; j < M; ++j) {
+    const float cx = __ldg(xyz + (size_t)old * 3), cy = __ldg(xyz + (size_t)old * 3 + 1), cz = __ldg(xyz + (size_t)old * 3 + 2);
+    uint32_t bv = 0u, bt = 0xffffffffu;
+    for (int k = tid; k < N; k += FPS_BIG_THREADS) {
+      const float d = fps_dist(p.mode, __ldg(xyz + (size_t)k * 3), __ldg(xyz + (size_t)k * 3 + 1), __ldg(xyz + (size_t)k * 3 + 2),
+                               cx, cy, cz);
+      const float t = fminf(d, temp[k]);
+      temp[k] = t;
+      uint32_t tk = (uint32_t)k;
+      if (p.mode == 0) {
+        const uint32_t r = (p.ref_log2 == 0) ? 0u : (__brev((uint32_t)(k % p.ref_bs)) >> (32 - p.ref_log2));
+        tk = (r << 16) | (uint32_t)(k / p.ref_bs);
+      }
+      const uint32_t u = __float_as_uint(t);
+      if (u > bv || (u == bv && tk < bt)) { bv = u; bt = tk; }
+    }
+    uint32_t wv = __reduce_max_sync(L3D_FULL_MASK, bv);
+    uint32_t wc = __reduce_max_sync(L3D_FULL_MASK, (bv == wv) ? ~bt : 0u);
+    const int buf = j & 1;
+    if (lane == 0) s_r[buf][warp] = make_uint2(wv, wc);
+    __syncthreads();
+    const uint2 e = s_r[buf][lane];                       // 32 warps: one entry per lane
+    wv = __reduce_max_sync(L3D_FULL_MASK, e.x);
+    wc = __reduce_max_sync(L3D_FULL_MASK, (e.x == wv) ? e.y : 0u);
+    const uint32_t wtk = ~wc;
+    if (p.mode == 0) {
+      const uint32_t r = (p.ref_log2 == 0) ? 0u : (__brev(wtk >> 16) >> (32 - p.ref_log2));
+      old = (int)((wtk & 0xffffu) * (uint32_t)p.ref_bs + r);
+    } else {
+      old = (int)wtk;
+    }
+    if (tid == 0) {
+      if (p.idx64) reinterpret_cast<long long*>(p.out)[(size_t)b * M + j] = old;
+      else reinterpret_cast<int*>(p.out)[(size_t)b * M + j] = old;
+    }
+  }
+}
+
 static int fps_launch(FpsParams p, cudaStream_t s) {
   if (!p.xyz || !p.out || p.B < 0 || p.N < 1 || p.M < 0) return L3D_ERR_INVALID;
   if (p.B == 0 || p.M == 0) return L3D_OK;   // `if (m <= 0) return;` (sampling_gpu.cu:99)
-  if (p.N > 16 * FPS_THREADS || p.N > 65536) return L3D_ERR_UNSUPPORTED;
   // the reference's launch width: opt_n_threads(n) = max(min(1 << int(log(n)/log(2)), 1024), 1)
   const int pow_2 = (int)(std::log(static_cast<double>(p.N)) / std::log(2.0));
   int bs = 1 << pow_2;
@@ -161,6 +220,19 @@ static int fps_launch(FpsParams p, cudaStream_t s) {
   p.ref_bs = bs;
   p.ref_log2 = 0;
   while ((1 << p.ref_log2) < bs) ++p.ref_log2;
+  if (p.N > 16 * FPS_THREADS) {
+    if ((long)p.N > 65535L * p.ref_bs) return L3D_ERR_UNSUPPORTED;   // 16-bit per-thread element counter of the tie key
+    float* scratch = nullptr;
+    if (!p.temp) {
+      cudaError_t e = cudaMallocAsync((void**)&scratch, (size_t)p.B * p.N * sizeof(float), s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    fps_stream_kernel<<<p.B, FPS_BIG_THREADS, 0, s>>>(p, scratch);
+    count_launch();
+    const cudaError_t le = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, s);
+    return le == cudaSuccess ? L3D_OK : (int)le;
+  }
   const int ppt = (p.N + FPS_THREADS - 1) / FPS_THREADS;
   const size_t smem = (size_t)p.N * 3 * sizeof(float);   // <= 96 KB (N <= 8192)
   if (smem > 40 * 1024) {   // (static shared memory also counts against the 48 KB default)

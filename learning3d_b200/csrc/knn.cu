@@ -783,6 +783,95 @@ __global__ void L3D_KNN_BOUNDS knn_kernel(const KnnParams p) {
   }
 }
 
+// ---- clouds beyond the shared-memory-resident path (N > L3D_KNN_MAX_N): streaming selection -------------------------
+// The reference's knn() is torch.matmul + topk and has no size limit (model_common_utils.py:3-9); the resident kernel
+// above keeps the whole candidate cloud in shared memory.  Here the cloud is streamed through a 32 KB tile, one query
+// row per warp, and every warp keeps its running top-k as a sorted list of 64-bit composites (same key arithmetic,
+// same (key desc, index asc) order as every other path).  Candidates arrive in index order, so a candidate enters the
+// list only when its composite beats the current k-th entry; the expected number of insertions per row is
+// ~k (1 + ln(N / k)), against N key evaluations.
+constexpr int KNN_STREAM_TILE = 2048;
+constexpr int KNN_STREAM_WARPS = 8;
+constexpr int KNN_STREAM_MAX_K = 2048;
+
+__host__ __device__ inline size_t knn_stream_smem_bytes(int k) {
+  return (size_t)KNN_STREAM_TILE * 16 + (size_t)KNN_STREAM_WARPS * (size_t)((k + 31) & ~31) * 8;
+}
+
+template <int MODE, bool SELF, bool CAND_BCN>
+__global__ void __launch_bounds__(KNN_STREAM_WARPS * 32) knn_stream_kernel(const KnnParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* tile = reinterpret_cast<float4*>(smem);
+  const int N = p.N, M = p.M, k = p.k;
+  const int kpad = (k + 31) & ~31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(tile + KNN_STREAM_TILE) + (size_t)warp * kpad;
+
+  const int row_blocks = (M + KNN_STREAM_WARPS - 1) / KNN_STREAM_WARPS;
+  const int b = (int)(blockIdx.x / row_blocks);
+  const int m = (int)(blockIdx.x % row_blocks) * KNN_STREAM_WARPS + warp;
+  const bool live = m < M;
+  const long row = (long)b * M + m;
+  const float* src = p.cand + (size_t)b * 3 * N;
+
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    if (SELF) {
+      q = CAND_BCN ? knn_pack<MODE>(src[m], src[(size_t)N + m], src[2 * (size_t)N + m])
+                   : knn_pack<MODE>(src[3 * (size_t)m], src[3 * (size_t)m + 1], src[3 * (size_t)m + 2]);
+    } else {
+      const float* qp = p.query + row * 3;
+      q = knn_pack<MODE>(qp[0], qp[1], qp[2]);
+    }
+  }
+  for (int i = lane; i < kpad; i += 32) list[i] = 0ull;     // below every real composite
+  __syncwarp();
+  unsigned long long kth = 0ull;
+
+  for (int t0 = 0; t0 < N; t0 += KNN_STREAM_TILE) {
+    const int cnt = min(KNN_STREAM_TILE, N - t0);
+    __syncthreads();                                          // the previous tile has been consumed
+    for (int i = tid; i < cnt; i += KNN_STREAM_WARPS * 32) {
+      const size_t j = (size_t)t0 + i;
+      tile[i] = CAND_BCN ? knn_pack<MODE>(src[j], src[(size_t)N + j], src[2 * (size_t)N + j])
+                         : knn_pack<MODE>(src[3 * j], src[3 * j + 1], src[3 * j + 2]);
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+      const int j = j0 + lane;
+      const unsigned long long c = (j < cnt) ? pack_pair(knn_key<MODE>(q, tile[j]), (uint32_t)(t0 + j)) : 0ull;
+      unsigned todo = __ballot_sync(L3D_FULL_MASK, c > kth);
+      while (todo) {
+        const int from = __ffs(todo) - 1;                     // lowest index first: equal keys keep their index order
+        todo &= todo - 1;
+        const unsigned long long cc = shfl_u64(c, from);
+        if (cc <= kth) continue;                              // the threshold rose since the ballot
+        int pos = 0;                                          // entries strictly better than cc
+        for (int base = 0; base < k; base += 32) {
+          const unsigned long long e = (base + lane < k) ? list[base + lane] : 0ull;
+          const int n = __popc(__ballot_sync(L3D_FULL_MASK, e > cc));
+          pos += n;
+          if (n < 32) break;
+        }
+        for (int hi = k - 1; hi > pos; hi -= 32) {            // shift [pos, k-2] one slot down the list, top chunk first
+          const int i = hi - lane;
+          const unsigned long long v = (i > pos) ? list[i - 1] : 0ull;
+          __syncwarp();
+          if (i > pos) list[i] = v;
+          __syncwarp();
+        }
+        if (lane == 0) list[pos] = cc;
+        __syncwarp();
+        kth = list[k - 1];
+      }
+    }
+  }
+  if (!live) return;
+  __syncwarp();
+  for (int pos = lane; pos < k; pos += 32) knn_store_packed(p, row, pos, list[pos]);
+}
+
 // ---- host side -----------------------------------------------------------------------
 static thread_local int g_force_slow = 0;   // testing hooks are per host thread
 int knn_force_slow_flag() { return g_force_slow; }   // knn_matrix.cu shares the testing hook
@@ -868,12 +957,46 @@ static int knn_launch_t(KnnParams p, cudaStream_t stream) {
   return L3D_OK;
 }
 
+extern "C" int l3d_graph_feature(const float* x_dev, const int64_t* idx_dev, int B, int C, int N, int k,
+                                 float* out_dev, void* stream);
+
+template <int MODE, bool SELF, bool CAND_BCN>
+static int knn_stream_launch(KnnParams p, cudaStream_t stream) {
+  if (p.k > KNN_STREAM_MAX_K) return L3D_ERR_UNSUPPORTED;
+  if (p.idx64 == 2 && p.N > 65536) return L3D_ERR_UNSUPPORTED;          // 16-bit wire format of the host path
+  auto kern = knn_stream_kernel<MODE, SELF, CAND_BCN>;
+  const size_t smem = knn_stream_smem_bytes(p.k);
+  if (smem > 48 * 1024) {
+    // per-(device, function) attribute: raise it once to the largest size this path can ask for, under a lock
+    static std::mutex mu;
+    static uint64_t done_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 64 || !(done_mask >> dev & 1)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)knn_stream_smem_bytes(KNN_STREAM_MAX_K));
+      if (e != cudaSuccess) return (int)e;
+      if (dev < 64) done_mask |= (uint64_t)1 << dev;
+    }
+  }
+  const long row_blocks = ((long)p.M + KNN_STREAM_WARPS - 1) / KNN_STREAM_WARPS;
+  const long grid = (long)p.B * row_blocks;
+  if (grid > 0x7fffffffL) return L3D_ERR_UNSUPPORTED;
+  kern<<<(unsigned)grid, KNN_STREAM_WARPS * 32, smem, stream>>>(p);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  if (p.feat_out)   // get_graph_feature on the finished indices (the fused variant needs the cloud resident on chip)
+    return l3d_graph_feature(p.cand, (const int64_t*)p.out_idx, p.B, 3, p.N, p.k, p.feat_out, (void*)stream);
+  return L3D_OK;
+}
+
 template <int MODE, bool SELF, bool CAND_BCN>
 static int knn_launch(KnnParams p, cudaStream_t stream) {
   if (p.B < 0 || p.N < 1 || p.M < 0 || p.k < 1 || p.k > p.N) return L3D_ERR_INVALID;
   if ((long)p.B * p.M == 0) return L3D_OK;   // empty batch: nothing to do (its pointers may be null)
   if (!p.cand || !p.out_idx || (!SELF && !p.query)) return L3D_ERR_INVALID;
-  if (p.N > L3D_KNN_MAX_N) return L3D_ERR_UNSUPPORTED;
+  if (p.N > L3D_KNN_MAX_N) return knn_stream_launch<MODE, SELF, CAND_BCN>(p, stream);   // streamed, any N
   // k > 128 (the reference's pointnet2 knn allows 200, torch.topk any k): beyond the survivor buffers of the
   // threshold scheme -> every row takes the exact k-round arg-max scan (O(k N) per row, same ordering rule)
   p.force_slow = (g_force_slow || p.k > 128) ? 1 : 0;

@@ -90,6 +90,7 @@ struct SoftCorrParams {
   const float* corr;      // [B, 3, Ns]  src_corr of the forward
   float* ds;              // optional [B, Ns, Nt]
   float* ds_t;            // optional [B, Nt, Ns]
+  int tma4;               // TMA pipeline: the tensor maps are the chunked 4-D views (one instruction per operand tile)
   int kmajor;             // generic pipeline only: operands are [B, N, D] (channels contiguous) instead of [B, D, N]
   int* err;               // device error word (0 = ok)
   float* part;            // split target range only: partial softmax states [B, Ns, gridDim.z, 8]
@@ -580,14 +581,21 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
       if (lane == 0) {
         const uint32_t st = tiles_s + s * SC_STAGE_BYTES;
         mbar_arrive_expect_tx(&sh->tma_full[s], A_TILE + B_TILE);
+        if (p.tma4) {
+          // chunked 4-D maps (Ns, Nt multiples of 32): one instruction per operand tile
+          tma_load_4d(st, &tmap_a, 0, kb * SC_BK, i0 / 32, b, &sh->tma_full[s]);
+          tma_load_4d(st + 2 * A_TILE, &tmap_b, 0, kb * SC_BK, ((jb0 + jb) * SC_BN + (int)crank * Cfg::BN_LOCAL) / 32, b,
+                      &sh->tma_full[s]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < SC_BM / 32; ++q)
-          tma_load_3d(st + q * Cfg::ATOM, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
-        // a pair member fetches only its half of the 256 target columns
+          for (int q = 0; q < SC_BM / 32; ++q)
+            tma_load_3d(st + q * Cfg::ATOM, &tmap_a, i0 + 32 * q, kb * SC_BK, b, &sh->tma_full[s]);
+          // a pair member fetches only its half of the 256 target columns
 #pragma unroll
-        for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
-          tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, (jb0 + jb) * SC_BN + (int)crank * Cfg::BN_LOCAL + 32 * q,
-                      kb * SC_BK, b, &sh->tma_full[s]);
+          for (int q = 0; q < Cfg::BN_LOCAL / 32; ++q)
+            tma_load_3d(st + 2 * A_TILE + q * Cfg::ATOM, &tmap_b, (jb0 + jb) * SC_BN + (int)crank * Cfg::BN_LOCAL + 32 * q,
+                        kb * SC_BK, b, &sh->tma_full[s]);
+        }
       }
       __syncwarp();
     }
@@ -621,6 +629,7 @@ static bool make_emb_tmap(CUtensorMap* m, const float* emb, int B, int D, int N)
 using namespace l3d;
 
 static thread_local int g_softcorr_force_generic = 0;   // testing hooks are per host thread
+static thread_local int g_softcorr_tma3 = 0;            // 1: keep the 3-D maps (32-point boxes) on aligned shapes too
 
 // -1: never split the target range, 0: automatic (small batches), > 0: forced number of splits (testing hook)
 static thread_local int g_softcorr_split = 0;
@@ -678,8 +687,15 @@ static int sc_launch(SoftCorrParams p, void* stream) {
              (((uintptr_t)p.src_emb | (uintptr_t)p.tgt_emb) & 15) == 0;
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma)); memset(&mb, 0, sizeof(mb));
-  if (tma) tma = make_emb_tmap(&ma, p.src_emb, p.B, p.D, p.Ns) && make_emb_tmap(&mb, p.tgt_emb, p.B, p.D, p.Nt);
   const bool pair = tma && g_softcorr_force_generic != 2 && p.Ns > SC_BM;
+  p.tma4 = 0;
+  if (tma && g_softcorr_tma3 == 0 && (p.Ns % 32 == 0) && (p.Nt % 32 == 0)) {
+    constexpr int BK = SoftCorrCfg<true>::BK;
+    const int bchunks = (pair ? SoftCorrCfg<true, 2>::BN_LOCAL : SoftCorrCfg<true>::BN_LOCAL) / 32;
+    if (make_dn_tmap4(&ma, p.src_emb, p.B, p.D, p.Ns, BK, SC_BM / 32) && make_dn_tmap4(&mb, p.tgt_emb, p.B, p.D, p.Nt, BK, bchunks))
+      p.tma4 = 1;
+  }
+  if (tma && !p.tma4) tma = make_emb_tmap(&ma, p.src_emb, p.B, p.D, p.Ns) && make_emb_tmap(&mb, p.tgt_emb, p.B, p.D, p.Nt);
 
   // Small batches: with one CTA (pair) per 128 (256) source rows a B = 2 call would occupy 8 of 74 TPCs.
   // Split the target tiles over gridDim.z so that about one wave of CTAs exists; each split leaves a
@@ -949,7 +965,13 @@ extern "C" int l3d_debug_soft_correspondence_tiles(float* host_out) {
 }
 
 // Testing hook: nonzero forces the generic (LDG producer) operand pipeline even for TMA-eligible shapes.
-extern "C" void l3d_debug_soft_correspondence_force_generic(int on) { g_softcorr_force_generic = on; }
+// 0: automatic, 1: generic (non-TMA) pipeline, 2: TMA without CTA pairs, 3: automatic but with the 3-D tensor maps
+// (32-point boxes) on shapes that would take the chunked 4-D maps — also honoured by edgeconv.cu
+extern "C" void l3d_debug_soft_correspondence_force_generic(int on) {
+  g_softcorr_force_generic = (on == 3) ? 0 : on;
+  g_softcorr_tma3 = (on == 3) ? 1 : 0;
+}
+namespace l3d { int tma3_boxes_forced() { return g_softcorr_tma3; } }
 
 // Testing hook: -1 = never split the target range over CTAs, 0 = automatic, n > 0 = force n splits.
 extern "C" void l3d_debug_soft_correspondence_split(int n) { g_softcorr_split = n; }

@@ -152,6 +152,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// 4-D variant for the chunked view of make_dn_tmap4 (coordinates: n inside the 32-chunk, channel, chunk, item)
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // L2 prefetch of one box (no shared memory, no barrier): hides HBM latency for tiles further ahead than the
 // shared-memory ring can hold (SASS: UTMAPF.L2)
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
@@ -209,6 +218,23 @@ inline bool make_dn_tmap(CUtensorMap* m, const float* base, int B, int D, int N,
   cuuint32_t box[3] = {32, (cuuint32_t)box_d, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The same tensor seen as [B, N/32, D, 32] (N % 32 == 0): dims (n_in = 32, d, chunk = n / 32, b) with strides
+// (4, 4N, 128, 4ND) bytes.  One box of (32, box_d, chunks, 1) lands in shared memory as `chunks` consecutive
+// [box_d x 32] atoms — byte for byte what `chunks` separate make_dn_tmap boxes at 32-point steps produce — so a whole
+// operand tile is ONE bulk-tensor instruction instead of 4-8 (the per-instruction cost of the TMA unit, not L2 or HBM
+// bandwidth, is what bounded the pipelines: profiles/r02/README.md).  Chunks beyond N/32 and channels beyond D read 0.
+inline bool make_dn_tmap4(CUtensorMap* m, const float* base, int B, int D, int N, int box_d, int chunks) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (N & 31) || chunks < 1 || chunks > 256) return false;
+  cuuint64_t dims[4] = {32, (cuuint64_t)D, (cuuint64_t)(N / 32), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)N * 4, 128, (cuuint64_t)N * (cuuint64_t)D * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_d, (cuuint32_t)chunks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -49,10 +49,59 @@ def test_maximum_cloud_size_and_beyond(oracle_mod):
     rng = np.random.default_rng(1)
     x = rng.random((1, 3, 8192), dtype=np.float32)                   # L3D_KNN_MAX_N: 8 candidate tiles
     assert np.array_equal(knn(T(x), 20).cpu().numpy(), oracle_mod.knn_expansion(x, 20, mt=True))
-    with pytest.raises(RuntimeError, match="not supported"):
-        knn(torch.rand(1, 3, 8196, device=DEV), 4)
     y = rng.random((1, 3, 700), dtype=np.float32)                    # k > 128: exact k-round scan path
     assert np.array_equal(knn(T(y), 200).cpu().numpy(), oracle_mod.knn_expansion(y, 200, mt=True))
+
+
+def test_clouds_beyond_the_resident_kernel_stream(oracle_mod):
+    """N > L3D_KNN_MAX_N (the reference's matmul + topk has no size limit): the streamed selection, every key mode,
+    bit-exact against the oracle including ties, k up to 200, the fused graph feature and the host entry point."""
+    from learning3d_b200 import _C
+    from learning3d_b200.utils import knn, get_graph_feature, knn_point
+    rng = np.random.default_rng(11)
+    for B, N, k in ((1, 8196, 4), (2, 10000, 20), (1, 8300, 200), (1, 20000, 33)):
+        x = rng.random((B, 3, N), dtype=np.float32)
+        assert np.array_equal(knn(T(x), k).cpu().numpy(), oracle_mod.knn_expansion(x, k, mt=True)), (B, N, k)
+    lat = rng.integers(0, 12, size=(1, 3, 9000)).astype(np.float32)          # a 12^3 lattice: every row is full of ties
+    assert np.array_equal(knn(T(lat), 20).cpu().numpy(), oracle_mod.knn_expansion(lat, 20, mt=True))
+    x = rng.random((1, 3, 8200), dtype=np.float32)
+    idx = knn(T(x), 6)
+    feat = get_graph_feature(T(x), k=6)                                        # knn + gather on this path
+    xt = torch.from_numpy(x).to(DEV)
+    nb = torch.gather(xt.unsqueeze(2).expand(1, 3, 8200, 8200), 3, idx.unsqueeze(1).expand(1, 3, 8200, 6))
+    want = torch.cat([nb, xt.unsqueeze(3).expand(1, 3, 8200, 6)], 1)
+    assert torch.equal(feat, want)
+    data = rng.random((2, 9001, 3), dtype=np.float32); q = rng.random((2, 77, 3), dtype=np.float32)
+    val, idx = knn_point(5, T(data), T(q))
+    ov, oi = oracle_mod.knn_point(5, data, q)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(val.cpu().numpy(), ov)
+    dd, qd = T(data), T(q)
+    for kk in (3, 64):
+        d2 = torch.empty((2, 77, kk), dtype=torch.float32, device=DEV)
+        i32 = torch.empty((2, 77, kk), dtype=torch.int32, device=DEV)
+        _C.check(_C.lib().l3d_pn2_knn(2, 77, 9001, kk, _C.ptr(qd), _C.ptr(dd), _C.ptr(d2), _C.ptr(i32), _C.stream()))
+        od2, oi = oracle_mod.pn2_knn(kk, q, data)
+        assert np.array_equal(i32.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od2)
+        i64 = torch.empty((2, 77, kk), dtype=torch.int64, device=DEV)
+        _C.check(_C.lib().l3d_knn_sqdist(_C.ptr(dd), _C.ptr(qd), 2, 9001, 77, kk, _C.ptr(i64), _C.stream()))
+        assert np.array_equal(i64.cpu().numpy(), oracle_mod.knn_sqdist(data, q, kk))
+    xh = torch.rand(2, 3, 9000)
+    ih = torch.empty(2, 9000, 8, dtype=torch.int64)
+    _C.check(_C.lib().l3d_knn_expansion_host(_C._P(xh.data_ptr()), 2, 9000, 8, _C._P(ih.data_ptr())))
+    assert np.array_equal(ih.numpy(), oracle_mod.knn_expansion(xh.numpy(), 8, mt=True))
+
+
+def test_fps_beyond_the_register_resident_kernel():
+    """N > 8192: running minima in `temp` (global), same rounds / tie rules as the resident kernel."""
+    from learning3d_b200.utils.lib import pointnet2_utils as pu
+    from learning3d_b200.utils.pointconv_util import farthest_point_sample
+    rng = np.random.default_rng(12)
+    x = rng.random((2, 9000, 3), dtype=np.float32)
+    assert np.array_equal(pu.furthest_point_sample(T(x), 96).cpu().numpy(), og.pn2_fps(x, 96)[0])
+    assert np.array_equal(farthest_point_sample(T(x), 50).cpu().numpy(), og.farthest_point_sample(x, 50))
+    lat = rng.integers(0, 6, size=(1, 8500, 3)).astype(np.float32)             # heavy ties
+    assert np.array_equal(pu.furthest_point_sample(T(lat), 40).cpu().numpy(), og.pn2_fps(lat, 40)[0])
+    assert np.array_equal(farthest_point_sample(T(lat), 40).cpu().numpy(), og.farthest_point_sample(lat, 40))
 
 
 def test_k_ranges_take_every_kernel_variant(oracle_mod):
@@ -92,8 +141,6 @@ def test_fps_extremes():
     assert all(sorted(r) == list(range(100)) for r in full)
     one = rng.random((1, 1, 3), dtype=np.float32)
     assert pu.furthest_point_sample(T(one), 1).item() == 0
-    with pytest.raises(RuntimeError, match="not supported"):
-        pu.furthest_point_sample(torch.rand(1, 8200, 3, device=DEV), 4)  # N > 8192
 
 
 def test_runs_on_a_side_stream(oracle_mod):
