@@ -434,10 +434,24 @@ int l3d_soft_correspondence_dscores(const float* src_emb_dev, const float* tgt_e
 int l3d_linear_cm(const float* wt_dev, const float* x_dev, const float* bias_dev, const float* residual_dev,
                   const float* col_div_dev, int B, int M, int K, int P, int relu, int w_heads, float* out_dev,
                   void* stream);
+/* l3d_linear_cm with the output transposed: out_dev [B, P, M] (positions major) — the attention value projection
+ * writes v^T [B, N_k, h*d_v], the per-head weight operand of the p.v product, directly. */
+int l3d_linear_cm_t(const float* wt_dev, const float* x_dev, const float* bias_dev, int B, int M, int K, int P, int relu,
+                    float* out_dev, void* stream);
 int l3d_attention_stats(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, int precise,
                         float* stats_dev, void* stream);
 int l3d_attention_probs_t(const float* q_dev, const float* k_dev, float* stats_dev, int BH, int D, int Nq, int Nk,
                           int normalized, float* probs_t_dev, void* stream);
+/* Bound-referenced softmax: l3d_attention_bounds writes stats_dev[(bh,i),0] = |q_i| max_j|k_j| log2(e)
+ * / sqrt(D) — an upper bound of the row's scaled scores, a valid exponent reference for l3d_attention_probs_t(normalized
+ * = 0) whenever it is <= 40 — and raises the flag in the LAST int of ws_dev (l3d_attention_bounds_ws_bytes) otherwise;
+ * l3d_attention_stats_if is l3d_attention_stats(precise = 0) that runs only when that flag is set (device-side
+ * decision, no host round trip). */
+size_t l3d_attention_bounds_ws_bytes(int BH);
+int l3d_attention_bounds(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, float* stats_dev,
+                         void* ws_dev, void* stream);
+int l3d_attention_stats_if(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, const int* flag_dev,
+                           float* stats_dev, void* stream);
 int l3d_layernorm_cm(const float* x_dev, const float* a2_dev, const float* b2_dev, float eps, int B, int D, int N,
                      float* out_dev, void* stream);
 /* Synchronises the device; returns and clears the pipeline error word of l3d_conv1x1_bn_relu_maxk (0 = ok). */

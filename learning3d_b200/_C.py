@@ -75,6 +75,10 @@ _SIGNATURES = {
     "l3d_edgeconv_status": [],
     "l3d_soft_correspondence_dscores": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "l3d_linear_cm": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "l3d_attention_bounds_ws_bytes": [_I],
+    "l3d_attention_bounds": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_attention_stats_if": [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "l3d_linear_cm_t": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "l3d_attention_stats": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "l3d_attention_probs_t": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "l3d_layernorm_cm": [_P, _P, _P, _F, _I, _I, _I, _P, _P],
@@ -96,6 +100,7 @@ _RESTYPE = {
     "l3d_emd_forward_ws_bytes": ctypes.c_size_t,
     "l3d_feature_square_distance_ws_bytes": ctypes.c_size_t,
     "l3d_sinkhorn_ws_bytes": ctypes.c_size_t,
+    "l3d_attention_bounds_ws_bytes": ctypes.c_size_t,
     "l3d_emd_backward_ws_bytes": ctypes.c_size_t,
 }
 

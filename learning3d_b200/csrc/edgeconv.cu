@@ -71,6 +71,7 @@ struct EdgeParams {
   int relu;
   const float* residual; // optional [B, M, P]: added after the activation (transformer sublayers: x + f(norm(x)))
   const float* col_div;  // optional [B, P]: every output column p is divided by col_div[b, p] (attention: p.v / row sum)
+  int out_t;             // linear layers: h_out is written transposed, [B, P, M] (v^T for the attention p.v product)
   int w4, x4;            // chunked 4-D tensor maps: weights; activations (bit 0: tiles at 32-position multiples, bit 1: +16)
   int w_heads;           // 0: one weight matrix for every item.  h > 0: item b uses rows (b % h)*M.. of weight batch b / h
 };
@@ -210,6 +211,16 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
             if (e < nv) v[e] = __fdividef(v[e], __ldg(cd + e));
         }
         if (!p.h_out) return;
+        if (GT == 1 && p.out_t) {
+          // [B, P, M]: for a fixed position the 32 lanes (consecutive channels) write one 128-byte line
+          if (vrow) {
+            float* dst = p.h_out + ((size_t)un.b * p.P + un.j0 + ch * 32) * p.M + c;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nv) dst[(size_t)e * p.M] = v[e];
+          }
+          return;
+        }
         if (vec) {
           // transpose the warp's 32 x 32 block through shared memory (16-byte chunk q of row r lives at chunk
           // q ^ (r & 7): conflict-free both ways): every store instruction then writes four 128-byte lines
@@ -248,6 +259,12 @@ edge_gemm_kernel(const EdgeParams p, const __grid_constant__ CUtensorMap tmap_w,
           else mbar_arrive(&sh->acc_empty[a]);
         }
       };
+      if (un.m0 + w4 * 32 >= p.M) {
+        // none of this warp's 32 accumulator lanes is an output channel (C_out = 64 fills half of the 128 lanes):
+        // nothing to read or store, only the accumulator hand-back
+        release();
+        continue;
+      }
       if (GT > 1 && nvalid == edge_tile_stride(GT > 1 ? GT : 2)) {
         // full tile, compile-time group size: every index below is static after unrolling — the pooled maxima
         // live in registers, the max chains of different groups are independent (ILP), no branches
@@ -616,7 +633,7 @@ static int edge_gemm_launch(const float* wt_dev, const float* x_dev, const float
   memset(&p, 0, sizeof(p));
   p.scale = scale_dev; p.shift = shift_dev; p.h_out = h_out_dev; p.pool_out = pool_out_dev;
   p.pool_bstride = (long)pool_bstride; p.pool_coff = pool_coff;
-  p.B = B; p.M = M; p.K = K; p.P = P; p.G = G; p.relu = relu;
+  p.B = B; p.M = M; p.K = K; p.P = P; p.G = G; p.relu = relu & 1; p.out_t = (relu >> 1) & 1;   // bit 1: transposed output
   p.residual = residual_dev; p.w_heads = w_heads; p.col_div = col_div_dev;
   if (pool_out_dev) {
     p.TS = edge_tile_stride(G);
@@ -728,7 +745,7 @@ extern "C" int l3d_conv1x1_bn_relu_maxk(const float* wt_dev, const float* x_dev,
                                         float* h_out_dev, float* pool_out_dev, long long pool_bstride, int pool_coff,
                                         void* stream) {
   if (!scale_dev) return L3D_ERR_INVALID;
-  return edge_gemm_launch(wt_dev, x_dev, scale_dev, shift_dev, nullptr, nullptr, 0, B, M, K, P, G, relu, h_out_dev,
+  return edge_gemm_launch(wt_dev, x_dev, scale_dev, shift_dev, nullptr, nullptr, 0, B, M, K, P, G, relu ? 1 : 0, h_out_dev,
                           pool_out_dev, pool_bstride, pool_coff, stream);
 }
 
@@ -744,8 +761,18 @@ extern "C" int l3d_linear_cm(const float* wt_dev, const float* x_dev, const floa
                              float* out_dev, void* stream) {
   if (!out_dev) return L3D_ERR_INVALID;
   if ((M * w_heads) & 3) return L3D_ERR_UNSUPPORTED;
-  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, residual_dev, col_div_dev, w_heads, B, M, K, P, 1, relu,
+  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, residual_dev, col_div_dev, w_heads, B, M, K, P, 1, relu ? 1 : 0,
                           out_dev, nullptr, 0, 0, stream);
+}
+
+// l3d_linear_cm with the output written transposed: out_dev [B, P, M] (positions major).  The attention value
+// projection uses it to produce v^T [B, N_k, h * d_v] — the per-head weight operand of the p.v product — without a
+// separate transpose pass.  No residual / column divide on this form.
+extern "C" int l3d_linear_cm_t(const float* wt_dev, const float* x_dev, const float* bias_dev, int B, int M, int K, int P,
+                               int relu, float* out_dev, void* stream) {
+  if (!out_dev) return L3D_ERR_INVALID;
+  return edge_gemm_launch(wt_dev, x_dev, nullptr, bias_dev, nullptr, nullptr, 0, B, M, K, P, 1, (relu ? 1 : 0) | 2, out_dev,
+                          nullptr, 0, 0, stream);
 }
 
 // Synchronises the device and returns (then clears) the pipeline error word of l3d_conv1x1_bn_relu_maxk:

@@ -90,6 +90,7 @@ struct SoftCorrParams {
   const float* corr;      // [B, 3, Ns]  src_corr of the forward
   float* ds;              // optional [B, Ns, Nt]
   float* ds_t;            // optional [B, Nt, Ns]
+  const int* cond_flag;   // EPI_STATS: when set and *cond_flag == 0 the launch returns at once (l3d_attention_stats_if)
   int tma4;               // TMA pipeline: the tensor maps are the chunked 4-D views (one instruction per operand tile)
   int kmajor;             // generic pipeline only: operands are [B, N, D] (channels contiguous) instead of [B, D, N]
   int* err;               // device error word (0 = ok)
@@ -197,6 +198,8 @@ softcorr_kernel(const SoftCorrParams p, const __grid_constant__ CUtensorMap tmap
   const uint32_t tiles_s = smem_u32(tiles);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // conditional statistics pass: every thread of every CTA reads the same word before anything is set up
+  if (EPI == EPI_STATS && p.cond_flag && *reinterpret_cast<const volatile int*>(p.cond_flag) == 0) return;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * SC_BM;
   // target tiles of this CTA: blockIdx.z selects a contiguous group of p.tiles_per_split tiles (small
@@ -908,6 +911,87 @@ extern "C" int l3d_attention_stats(const float* q_dev, const float* k_dev, int B
   p.single_pass = precise ? 0 : 1;
   return sc_launch<EPI_STATS>(p, stream);
 }
+// ---- bound-referenced softmax -----------------------------------------------------------------------------------
+// The exponent reference of a softmax row does not have to be the row maximum: any m_i with
+// max_j s_ij - m_i in (-~100, 0] (log2 units) gives the same probabilities after normalisation, without overflow or
+// underflow.  Cauchy-Schwarz supplies one for free:  |q_i . k_j| <= |q_i| max_j |k_j|, so
+// m_i = |q_i| * max_j |k_j| * log2(e) / sqrt(D) >= every scaled score of the row, and the row maximum is at least
+// -m_i.  Whenever m_i <= ATTN_BOUND_MAX for every row of the call (2 m_i <= 80: the largest term is >= 2^-80), the
+// statistics pass is unnecessary; otherwise a device flag is raised and l3d_attention_stats_if computes the true
+// maxima.  Nothing comes back to the host.
+constexpr float ATTN_BOUND_MAX = 40.0f;
+
+// thread = key j: |k_j| over the D channels of x [BH, D, N] (coalesced over j); block max -> atomicMax on the bits
+static __global__ void attn_colnorm_max_kernel(const float* __restrict__ x, int D, int N, unsigned int* __restrict__ out_max) {
+  const int bh = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (j < N) {
+    const float* px = x + (size_t)bh * D * N + j;
+    for (int d = 0; d < D; ++d) { const float v = px[(size_t)d * N]; acc = fmaf(v, v, acc); }
+  }
+  float nrm = sqrtf(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nrm = fmaxf(nrm, __shfl_xor_sync(L3D_FULL_MASK, nrm, o));
+  if ((threadIdx.x & 31) == 0 && !(nrm <= 0.f)) atomicMax(out_max + bh, __float_as_uint(nrm));   // NaN propagates too
+}
+
+// thread = query i: m_i = |q_i| * kmax[bh] * c (rounded up a little) -> stats[(bh, i), 0]; raises *flag when too large
+static __global__ void attn_row_bound_kernel(const float* __restrict__ q, int D, int N, const unsigned int* __restrict__ kmax,
+                                             float c, float* __restrict__ stats, int* __restrict__ flag) {
+  const int bh = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* pq = q + (size_t)bh * D * N + i;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) { const float v = pq[(size_t)d * N]; acc = fmaf(v, v, acc); }
+  const float m = sqrtf(acc) * __uint_as_float(kmax[bh]) * c * 1.0001f;
+  stats[((size_t)bh * N + i) * 2] = m;
+  if (!(m <= ATTN_BOUND_MAX)) atomicOr(flag, 1);      // also raised by NaN / Inf
+}
+
+extern "C" size_t l3d_attention_bounds_ws_bytes(int BH) { return BH < 0 ? 0 : sizeof(int) * ((size_t)BH + 1); }
+
+// q_dev [BH, D, Nq], k_dev [BH, D, Nk] -> stats_dev[(bh, i), 0] = the row's exponent reference (an upper bound of its
+// scaled scores); ws_dev (l3d_attention_bounds_ws_bytes) receives max_j |k_j| per head and, in its LAST int, the flag
+// "some row's bound is too loose: run the statistics pass" consumed by l3d_attention_stats_if.
+extern "C" int l3d_attention_bounds(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk, float* stats_dev,
+                                    void* ws_dev, void* stream) {
+  if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
+  if (BH == 0 || Nq == 0) return L3D_OK;
+  if (!q_dev || !k_dev || !stats_dev || !ws_dev) return L3D_ERR_INVALID;
+  if (BH > 65535) return L3D_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* kmax = (unsigned int*)ws_dev;
+  int* flag = (int*)ws_dev + BH;
+  cudaError_t e = cudaMemsetAsync(ws_dev, 0, sizeof(int) * ((size_t)BH + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  attn_colnorm_max_kernel<<<dim3((unsigned)((Nk + 255) / 256), (unsigned)BH), 256, 0, st>>>(k_dev, D, Nk, kmax);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  const float c = (float)(1.4426950408889634 / sqrt((double)D));
+  attn_row_bound_kernel<<<dim3((unsigned)((Nq + 255) / 256), (unsigned)BH), 256, 0, st>>>(q_dev, D, Nq, kmax, c, stats_dev, flag);
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+// l3d_attention_stats(precise = 0) that runs only if *flag_dev != 0 (flag_dev = the last int of l3d_attention_bounds'
+// workspace); when it runs it replaces the bounds in stats_dev[.., 0] by the true row maxima.
+extern "C" int l3d_attention_stats_if(const float* q_dev, const float* k_dev, int BH, int D, int Nq, int Nk,
+                                      const int* flag_dev, float* stats_dev, void* stream) {
+  if (BH < 0 || D < 1 || Nq < 0 || Nk < 1) return L3D_ERR_INVALID;
+  if (BH == 0 || Nq == 0) return L3D_OK;
+  if (!q_dev || !k_dev || !stats_dev || !flag_dev) return L3D_ERR_INVALID;
+  SoftCorrParams p;
+  memset(&p, 0, sizeof(p));
+  p.src_emb = q_dev; p.tgt_emb = k_dev; p.stats = stats_dev;
+  p.B = BH; p.D = D; p.Ns = Nq; p.Nt = Nk;
+  p.single_pass = 1;
+  p.cond_flag = flag_dev;
+  return sc_launch<EPI_STATS>(p, stream);
+}
+
 // ... + stats_dev -> probs_t_dev [BH, Nk, Nq] = softmax(q^T k / sqrt(D), over k) transposed
 extern "C" int l3d_attention_probs_t(const float* q_dev, const float* k_dev, float* stats_dev, int BH, int D, int Nq,
                                      int Nk, int normalized, float* probs_t_dev, void* stream) {

@@ -38,6 +38,17 @@ def linear_cm(x, lin, relu=False, residual=None):
     return out
 
 
+def linear_cm_t(x, lin):
+    """x [B, K, N] -> lin(x^T) [B, N, M], i.e. the position-major result, written directly by the GEMM epilogue."""
+    wt, bias = _wt(lin)
+    B, K, N = x.shape
+    M = wt.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().l3d_linear_cm_t(_C.ptr(wt), _C.ptr(x), _C.ptr(bias), B, M, K, N, 0, _C.ptr(out), _C.stream()),
+             "linear (transposed output)")
+    return out
+
+
 def layernorm_cm(x, norm):
     B, D, N = x.shape
     out = torch.empty_like(x)
@@ -55,17 +66,20 @@ def attention_cm(attn, xq, xkv, residual):
     h, dk = attn.h, attn.d_k
     q = linear_cm(xq, attn.linears[0])
     k = linear_cm(xkv, attn.linears[1])
-    v = linear_cm(xkv, attn.linears[2])
+    vt = linear_cm_t(xkv, attn.linears[2])                    # v^T [B, Nk, h*d_k]: heads side by side
     st = _C.stream()
     stats = torch.empty((B * h, Nq, 2), dtype=torch.float32, device=xq.device)
-    # pass 1: row maxima from ONE TF32 MMA pass (only an exponent reference); pass 2: 3xTF32 scores again,
-    # unnormalised probabilities 2^(s - max) written transposed + the exact row sums
-    _C.check(lib.l3d_attention_stats(_C.ptr(q), _C.ptr(k), B * h, dk, Nq, Nk, 0, _C.ptr(stats), st), "attention stats")
+    # exponent reference of every row: the Cauchy-Schwarz bound |q_i| max_j |k_j| / sqrt(d_k) (two small launches);
+    # the statistics pass proper (row maxima from ONE TF32 MMA pass) only runs if some bound is too loose — decided on
+    # the device.  Pass 2: 3xTF32 scores, unnormalised probabilities 2^(s - m_i) written transposed + exact row sums.
+    ws = torch.empty(B * h + 1, dtype=torch.int32, device=xq.device)
+    _C.check(lib.l3d_attention_bounds(_C.ptr(q), _C.ptr(k), B * h, dk, Nq, Nk, _C.ptr(stats), _C.ptr(ws), st), "attention bounds")
+    _C.check(lib.l3d_attention_stats_if(_C.ptr(q), _C.ptr(k), B * h, dk, Nq, Nk, _C._P(ws.data_ptr() + 4 * B * h),
+                                        _C.ptr(stats), st), "attention stats")
     probs_t = torch.empty((B * h, Nk, Nq), dtype=torch.float32, device=xq.device)
     _C.check(lib.l3d_attention_probs_t(_C.ptr(q), _C.ptr(k), _C.ptr(stats), B * h, dk, Nq, Nk, 0, _C.ptr(probs_t), st),
              "attention probabilities")
     rowsum = stats[:, :, 1].contiguous()                        # [B*h, Nq]
-    vt = v.transpose(1, 2).contiguous()                       # [B, Nk, h*d_k]: v^T, heads side by side
     ctx = torch.empty((B, d, Nq), dtype=torch.float32, device=xq.device)      # = [B*h, d_k, Nq]
     _C.check(lib.l3d_linear_cm(_C.ptr(vt), _C.ptr(probs_t), _C.ptr(None), _C.ptr(None), _C.ptr(rowsum), B * h, dk, Nk,
                                Nq, 0, h, _C.ptr(ctx), st), "attention p.v")

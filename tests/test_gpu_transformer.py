@@ -31,6 +31,16 @@ def test_linear_cm_bias_relu_residual():
             assert err < 4e-6, (B, K, M, N, relu, err)
 
 
+def test_linear_cm_transposed_output_is_the_same_numbers():
+    """l3d_linear_cm_t writes [B, N, M]: bit-identical to the transpose of l3d_linear_cm's result."""
+    from learning3d_b200.utils.transformer_fused import linear_cm, linear_cm_t
+    torch.manual_seed(7)
+    for (B, K, M, N) in [(3, 512, 512, 1024), (2, 72, 200, 132), (1, 512, 512, 260)]:
+        lin = torch.nn.Linear(K, M).to(DEV)
+        x = torch.randn(B, K, N, device=DEV)
+        assert torch.equal(linear_cm_t(x, lin), linear_cm(x, lin).transpose(1, 2).contiguous()), (B, K, M, N)
+
+
 def test_layernorm_cm():
     from learning3d_b200.utils.transformer import _Norm
     from learning3d_b200.utils.transformer_fused import layernorm_cm
@@ -126,3 +136,38 @@ def test_attention_protocols_agree():
     print("attention protocols: precise %.3g, fast %.3g, between %.3g" % (errs[0], errs[1], (outs[0] - outs[1]).abs().max().item()))
     assert max(errs) < 6e-5
     assert (outs[0] - outs[1]).abs().max().item() < 6e-5
+
+
+def test_bound_referenced_softmax_and_its_fallback():
+    """l3d_attention_bounds: the Cauchy-Schwarz row bound as the exponent reference (no statistics pass); with large
+    scores the device flag is raised and l3d_attention_stats_if replaces the bounds by the true maxima."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    torch.manual_seed(13)
+    BH, D, Nq, Nk = 8, 128, 260, 512
+    st = _C.stream()
+    for scale, want_flag in ((1.0, 0), (25.0, 1)):
+        q = torch.randn(BH, D, Nq, device=DEV) * scale; k = torch.randn(BH, D, Nk, device=DEV)
+        stats = torch.full((BH, Nq, 2), float("nan"), device=DEV)
+        ws = torch.empty(BH + 1, dtype=torch.int32, device=DEV)
+        assert lib.l3d_attention_bounds_ws_bytes(BH) == 4 * (BH + 1)
+        _C.check(lib.l3d_attention_bounds(_C.ptr(q), _C.ptr(k), BH, D, Nq, Nk, _C.ptr(stats), _C.ptr(ws), st))
+        bound = stats[:, :, 0].clone()
+        s = torch.einsum("bdq,bdk->bqk", q.double(), k.double()) / math.sqrt(D) * math.log2(math.e)
+        assert (bound.double() >= s.max(-1).values).all()                       # a true upper bound of every row
+        assert int(ws[BH].item()) == want_flag, (scale, int(ws[BH].item()), bound.max().item())
+        _C.check(lib.l3d_attention_stats_if(_C.ptr(q), _C.ptr(k), BH, D, Nq, Nk, _C._P(ws.data_ptr() + 4 * BH), _C.ptr(stats), st))
+        if want_flag:
+            got_max = stats[:, :, 0].double()
+            assert ((got_max - s.max(-1).values).abs() <= 2e-3 * s.abs().max(-1).values + 1e-3).all()   # one TF32 pass
+        else:
+            assert torch.equal(stats[:, :, 0], bound)                           # the statistics launch returned at once
+        pt = torch.empty(BH, Nk, Nq, device=DEV)
+        _C.check(lib.l3d_attention_probs_t(_C.ptr(q), _C.ptr(k), _C.ptr(stats), BH, D, Nq, Nk, 0, _C.ptr(pt), st))
+        p = pt.double().transpose(1, 2) / stats[:, :, 1].double().unsqueeze(-1)
+        want = torch.softmax(s * math.log(2.0), dim=-1)
+        assert torch.isfinite(pt).all()
+        # a probability moves by (score error) x p: 3xTF32 scores carry <= ~4e-6 * sum|q||k|
+        tol = 2e-5 if scale == 1.0 else 2e-3
+        assert (p - want).abs().max().item() < tol, (scale, (p - want).abs().max().item())
+    assert lib.l3d_soft_correspondence_status() == 0
