@@ -25,6 +25,11 @@ def main(which):
         x = torch.rand(32, 3, 1024, device=DEV)
         for _ in range(5):
             knn(x, 20)
+    elif which == "knnstream":
+        from learning3d_b200.utils import knn
+        x = torch.rand(2, 3, 16384, device=DEV)           # beyond the resident kernel: streamed selection
+        for _ in range(3):
+            knn(x, 20)
     elif which == "dcp":
         from learning3d_b200.models import DCP, DGCNN
         net = DCP(feature_model=DGCNN(emb_dims=512), cycle=True).to(DEV).eval()

@@ -76,7 +76,7 @@ def main():
             md += launch_table(p, title)
     md += ["## `ncu --set full` captures", "",
            "| family | kernel | grid x block | " + " | ".join(h for _, h in FIELDS) + " |", "|---|---|---|" + "---|" * len(FIELDS)]
-    for fam in ("knn32", "edge", "emd", "attn", "group", "misc", "rpm", "chamfer"):
+    for fam in ("knn32", "knnstream", "edge", "emd", "attn", "group", "misc", "rpm", "chamfer"):
         p = os.path.join(GO, "r02_%s.log" % fam)
         if not os.path.exists(p):
             continue

@@ -168,3 +168,35 @@ def test_dgcnn_forward_fused_vs_reference_layers(emb, B, N):
     y = net(x)
     y.mean().backward()
     assert net.conv1.weight.grad is not None
+
+
+def test_chunked_tensor_maps_move_the_same_bytes():
+    """The 4-D tensor maps (one bulk-tensor instruction per operand tile, tc05.cuh:make_dn_tmap4) must fill shared memory
+    exactly like the 32-point boxes they replace: results bit-identical, including the k = 20 tiles that start 16
+    positions past a chunk boundary (shifted map) and the ragged last tile of a row (falls back to the boxes)."""
+    from learning3d_b200 import _C
+    lib = _C.lib()
+    torch.manual_seed(21)
+    cases = [(2, 64, 64, 5120, 20), (2, 256, 128, 2560, 20), (1, 128, 64, 1024 * 16, 16), (2, 512, 512, 1024, 1), (1, 64, 64, 20 * 112, 20), (1, 64, 64, 20 * 77, 20)]
+    try:
+        for (B, M, K, P, G) in cases:
+            wt = torch.randn(K, M, device=DEV) * 0.2
+            x = torch.randn(B, K, P, device=DEV)
+            sc = torch.rand(M, device=DEV) + 0.5
+            sh = torch.randn(M, device=DEV) * 0.1
+            res = []
+            for mode in (3, 0):                                   # 3: force the 32-point boxes, 0: automatic
+                lib.l3d_debug_soft_correspondence_force_generic(mode)
+                res.append(_layer(wt, x, sc, sh, G, want_h=(M <= 128 or G == 1), want_pool=(G > 1)))
+            for a, b in zip(res[0], res[1]):
+                assert (a is None and b is None) or torch.equal(a, b), (B, M, K, P, G)
+        src = torch.randn(3, 512, 1024, device=DEV); tgt = torch.randn(3, 512, 1024, device=DEV); xyz = torch.randn(3, 3, 1024, device=DEV)
+        outs = []
+        for mode in (3, 0):
+            lib.l3d_debug_soft_correspondence_force_generic(mode)
+            o = torch.empty(3, 3, 1024, device=DEV)
+            _C.check(lib.l3d_soft_correspondence(_C.ptr(src), _C.ptr(tgt), _C.ptr(xyz), 3, 512, 1024, 1024, _C.ptr(o), _C.stream()))
+            outs.append(o)
+        assert torch.equal(outs[0], outs[1]) and lib.l3d_soft_correspondence_status() == 0
+    finally:
+        lib.l3d_debug_soft_correspondence_force_generic(0)
