@@ -23,6 +23,7 @@ _SIGNATURES = {
     "l3d_error_string": [_I],
     "l3d_launch_count": [],
     "l3d_debug_force_slow_path": [_I],
+    "l3d_debug_knn_path": [_I],
     "l3d_knn_expansion": [_P, _I, _I, _I, _P, _P, _P],
     "l3d_knn_expansion_host": [_P, _I, _I, _I, _P],
     "l3d_knn_graph_feature": [_P, _I, _I, _I, _P, _P, _P],
@@ -92,6 +93,7 @@ _RESTYPE = {
     "l3d_error_string": ctypes.c_char_p,
     "l3d_launch_count": ctypes.c_uint64,
     "l3d_debug_force_slow_path": None,
+    "l3d_debug_knn_path": None,
     "l3d_debug_emd_force_multilaunch": None,
     "l3d_debug_soft_correspondence_force_generic": None,
     "l3d_debug_soft_correspondence_split": None,

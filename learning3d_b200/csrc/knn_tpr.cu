@@ -1,0 +1,621 @@
+// Thread-per-row fused pairwise-distance + top-k (sm_100a): knn() on xyz clouds, k <= 24, large batches.
+//
+// Replaces knn() utils/model_common_utils.py:3-9 (same keys, same (key desc, index asc) order as knn.cu —
+// bit-identical results, the test-suite compares the two kernels against each other and against the oracle).
+//
+// Why a second kernel ("round 2, second half"): knn.cu gives a warp two query rows and spreads
+// the candidates over the lanes, so every step of the selection (lane-maximum sort, survivor scan, final sort)
+// is a chain of warp shuffles: ~64 SHFL + 65 ISETP + 48 SEL per row, issue slots 53 % busy, and neither fewer
+// arithmetic instructions (packed fp32) nor more resident warps moved the clock.  Here a THREAD owns a query
+// row and a warp owns 32 consecutive rows of one cloud:
+//   * every candidate operand is a shared-memory BROADCAST (all lanes read the same 16 bytes: one wavefront),
+//     two candidates per packed FFMA2 as before;
+//   * the selection never leaves the thread's registers — no shuffles, no scans, no per-warp buffers:
+//       pass 1: the maxima of 64 candidate groups (one FMNMX3 per candidate pair);
+//       threshold: the k-th largest group maximum through an in-register bitonic network (2 x sort-32 +
+//         merge; FMNMX only) — at least k keys reach it and on average 23.5 do (never more than 32 in
+//         99.96 % of uniformly random rows);
+//       pass 2: the same packed expressions again (same bits), the sign of s - thr shifted into a 32-bit
+//         survivor mask per 32 candidates, the few set bits appended to a per-thread index list;
+//       final: the <= 32 survivors are re-evaluated with the full key formula (one gathered LDS.128 each),
+//         packed into the 64-bit (key, ~index) composites of common.cuh and sorted by an in-register
+//         bitonic network; lanes store their k indices with 128-bit stores.
+//   * rows whose list exceeds 32 entries sort a second block of 32 and merge (whole warp, rare); beyond 64
+//     (duplicate points, adversarial ties) the row is redone by the exact k-round scan of knn_common.cuh.
+// The price is parallelism: a row is a thread, so B*N/32 warps exist in total (1024 at C2 = 6.9 per SM) and
+// the kernel is one wave; the launcher therefore only takes this path when there are enough rows
+// (knn.cu: knn_launch), smaller batches stay on the warp-per-row-pair kernel.
+#include "knn_common.cuh"
+#include "../../include/l3d_b200.h"
+#include "launch_count.h"
+
+#include <math.h>
+#include <mutex>
+
+namespace l3d {
+
+constexpr int TPR_THREADS = 256;
+constexpr int TPR_WARPS = TPR_THREADS / 32;
+constexpr int TPR_G = 64;       // candidate groups per row (threshold = k-th largest group maximum)
+constexpr int TPR_CAP = 64;     // survivor-list entries per row (uint16 indices)
+constexpr int TPR_SLOTS = 2;    // clouds resident per CTA round
+constexpr int TPR_MIN_N = 128, TPR_MAX_N = 2048, TPR_MAX_K = 24;
+
+#ifndef L3D_TPR_EXTRACT
+#define L3D_TPR_EXTRACT 1     // 1: three predicated find-lowest-bit steps per mask word + rare loop; 0: plain loop
+#endif
+#ifndef L3D_TPR_FUSE_THR
+#define L3D_TPR_FUSE_THR 1    // 1: pass 2 evaluates s - thr inside the fma chain (no FADD2), threshold lowered by its error bound
+#endif
+#ifndef L3D_TPR_UNROLL_G
+#define L3D_TPR_UNROLL_G 2    // candidate groups per pass-1 loop trip
+#endif
+#ifndef L3D_TPR_STOP
+#define L3D_TPR_STOP 0       // profiling only: 1..4 = stop a unit after staging / pass 1 / threshold / pass 2
+#endif
+#ifndef L3D_TPR_DSETP
+#define L3D_TPR_DSETP 0       // 1: final sort compares 62-bit composites as positive doubles (DSETP on the fp64 pipe)
+#endif
+
+constexpr int TPR_UNROLL_G = L3D_TPR_UNROLL_G;
+constexpr size_t TPR_LIST_BYTES = (size_t)(TPR_CAP + 1) * TPR_THREADS * 2;   // + the entry dead stores land on once a list is full
+
+// shared memory per resident cloud: pair_xy + pair_zw (8 B per candidate each, npad entries) + float4 (x,y,z,|p|^2)
+// padded to whole KNN_TILEs (the warp-cooperative overflow routine of knn_common.cuh reads whole tiles)
+__host__ __device__ inline int tpr_npad(int N) { return (N + 127) & ~127; }
+__host__ __device__ inline int tpr_ntile(int N) { return ((N + KNN_TILE - 1) / KNN_TILE) * KNN_TILE; }
+__host__ __device__ inline size_t tpr_cloud_bytes(int N) { return (size_t)tpr_npad(N) * 16 + (size_t)tpr_ntile(N) * 16; }
+__host__ __device__ inline size_t tpr_smem_bytes(int N) {
+  return TPR_SLOTS * tpr_cloud_bytes(N) + TPR_LIST_BYTES + (size_t)TPR_G * TPR_THREADS * 4 +
+         (size_t)TPR_WARPS * 64 * 8 + 16;
+}
+
+// ---- in-register sorting networks (every index is a compile-time constant after unrolling) ----------------
+template <int N>
+__device__ __forceinline__ void reg_sort_desc(float (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = ((i & k) == 0) || k == N;
+          const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+          a[i] = up ? hi : lo;
+          a[l] = up ? lo : hi;
+        }
+      }
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void reg_merge_desc(float (&a)[N]) {   // a is bitonic -> descending
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int l = i ^ j;
+      if (l > i) {
+        const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+        a[i] = hi;
+        a[l] = lo;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void cex_u64(unsigned long long& x, unsigned long long& y, bool up) {
+  // one 64-bit comparison (ISETP + ISETP.EX) and four SELs per exchange.  Written in PTX: from C++ nvcc recognises
+  // the pair as umin/umax and emits a second, mirrored comparison for the minimum.
+  unsigned long long hi, lo;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.u64 p, %2, %3;\n\tselp.b64 %0, %2, %3, p;\n\tselp.b64 %1, %3, %2, p;\n\t}"
+      : "=l"(hi), "=l"(lo) : "l"(x), "l"(y));
+  x = up ? hi : lo;   // `up` is a compile-time constant after unrolling
+  y = up ? lo : hi;
+}
+template <int N>
+__device__ __forceinline__ void reg_sort_desc(unsigned long long (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) cex_u64(a[i], a[l], ((i & k) == 0) || k == N);
+      }
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void reg_merge_desc(unsigned long long (&a)[N]) {
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int l = i ^ j;
+      if (l > i) cex_u64(a[i], a[l], true);
+    }
+  }
+}
+
+// ---- final sort of the composites ---------------------------------------------------------------------------
+// L3D_TPR_DSETP: the composite is 62 bits, (ordered key << 30) | (~index & 0x3fffffff), so as an IEEE double it is a
+// non-negative finite number (or zero / denormal) whose numeric order is its bit-pattern order: one DSETP on the
+// fp64 pipe replaces the ISETP + ISETP.EX pair on the (busier) ALU pipe.
+#if L3D_TPR_DSETP
+__device__ __forceinline__ unsigned long long tpr_composite(float key, uint32_t idx) {
+  return ((unsigned long long)f32_order(key + 0.0f) << 30) | (unsigned long long)(~idx & 0x3fffffffu);
+}
+__device__ __forceinline__ uint32_t tpr_comp_index(unsigned long long c) { return ~(uint32_t)c & 0x3fffffffu; }
+__device__ __forceinline__ float tpr_comp_key(unsigned long long c) { return f32_unorder((uint32_t)(c >> 30)); }
+__device__ __forceinline__ void tpr_cex(unsigned long long& x, unsigned long long& y, bool up) {
+  unsigned long long hi, lo;
+  asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\tmov.b64 a, %2;\n\tmov.b64 b, %3;\n\tsetp.gt.f64 p, a, b;\n\t"
+      "selp.b64 %0, %2, %3, p;\n\tselp.b64 %1, %3, %2, p;\n\t}"
+      : "=l"(hi), "=l"(lo) : "l"(x), "l"(y));
+  x = up ? hi : lo;
+  y = up ? lo : hi;
+}
+#else
+__device__ __forceinline__ unsigned long long tpr_composite(float key, uint32_t idx) { return pack_pair(key, idx); }
+__device__ __forceinline__ uint32_t tpr_comp_index(unsigned long long c) { return ~(uint32_t)c; }
+__device__ __forceinline__ float tpr_comp_key(unsigned long long c) { return f32_unorder((uint32_t)(c >> 32)); }
+__device__ __forceinline__ void tpr_cex(unsigned long long& x, unsigned long long& y, bool up) { cex_u64(x, y, up); }
+#endif
+template <int N>
+__device__ __forceinline__ void tpr_sort_desc(unsigned long long (&a)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) tpr_cex(a[i], a[l], ((i & k) == 0) || k == N);
+      }
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void tpr_merge_desc(unsigned long long (&a)[N]) {
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int l = i ^ j;
+      if (l > i) tpr_cex(a[i], a[l], true);
+    }
+  }
+}
+
+// PPG: candidate pairs per group when known at compile time (8 <=> N = 1024), 0 = run-time.
+// KT:  k when known at compile time (20, DGCNN / DCP), 0 = run-time k <= 24.
+template <int PPG, int KT, bool FEAT>
+__global__ void __launch_bounds__(TPR_THREADS, 1) knn_tpr_kernel(const KnnParams p) {
+  constexpr int MODE = MODE_EXPANSION_NEG;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int N = p.N, k = KT ? KT : p.k;
+  const int npad = tpr_npad(N), ntile = tpr_ntile(N);
+  const int ppg = PPG ? PPG : npad / (2 * TPR_G);
+  const int nwords = npad / 32;
+  const int upc = N / 32;                       // warp units (32 consecutive rows) per cloud
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  unsigned char* tail = smem + TPR_SLOTS * tpr_cloud_bytes(N);
+  unsigned short* list = reinterpret_cast<unsigned short*>(tail) + tid;                 // [TPR_CAP][TPR_THREADS]
+  float* gmax = reinterpret_cast<float*>(tail + TPR_LIST_BYTES) + tid;   // [TPR_G][TPR_THREADS]
+  unsigned long long* cbuf = reinterpret_cast<unsigned long long*>(
+      tail + TPR_LIST_BYTES + (size_t)TPR_G * TPR_THREADS * 4) + warp * 64;
+  int* wmax = reinterpret_cast<int*>(tail + TPR_LIST_BYTES + (size_t)TPR_G * TPR_THREADS * 4 +
+                                     (size_t)TPR_WARPS * 64 * 8);                       // [TPR_SLOTS] max |c|^2 (float bits)
+
+  // programmatic dependent launch, as in knn.cu: the next launch may start filling SMs as our CTAs retire,
+  // and nothing touches global memory before the previous launch has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const long units = (long)p.B * upc;
+  long u0 = units * blockIdx.x / gridDim.x;
+  const long u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+  while (u0 < u1) {
+    const int b0 = (int)(u0 / upc);
+    const long round_end = min(u1, (long)(b0 + TPR_SLOTS) * upc);
+    const int nb = (int)((round_end - 1) / upc) - b0 + 1;
+
+    // ---- stage the clouds of this round: pair layout for the packed loops + float4 for the gathers -----
+    if (tid < TPR_SLOTS) wmax[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nb * (ntile / 2); i += TPR_THREADS) {
+      const int s = i / (ntile / 2), pi = i - s * (ntile / 2);
+      unsigned char* base = smem + (size_t)s * tpr_cloud_bytes(N);
+      ulonglong2* pxy = reinterpret_cast<ulonglong2*>(base);
+      ulonglong2* pzw = pxy + npad / 2;
+      float4* packed = reinterpret_cast<float4*>(pzw + npad / 2);
+      const float* src = p.cand + (size_t)(b0 + s) * 3 * N;
+      float4 c0 = knn_padding<MODE>(), c1 = knn_padding<MODE>();
+      if (2 * pi < N) {   // N is even: a pair is either real or padding
+        const float2 x = *reinterpret_cast<const float2*>(src + 2 * pi);
+        const float2 y = *reinterpret_cast<const float2*>(src + N + 2 * pi);
+        const float2 z = *reinterpret_cast<const float2*>(src + 2 * (size_t)N + 2 * pi);
+        c0 = knn_pack<MODE>(x.x, y.x, z.x);
+        c1 = knn_pack<MODE>(x.y, y.y, z.y);
+        atomicMax(&wmax[s], __float_as_int(fmaxf(c0.w, c1.w)));      // |c|^2 >= 0: integer order == float order
+      }
+      packed[2 * pi] = c0;
+      packed[2 * pi + 1] = c1;
+      if (2 * pi < npad) {
+        pxy[pi] = make_ulonglong2(f2_pack(c0.x, c1.x), f2_pack(c0.y, c1.y));
+        pzw[pi] = make_ulonglong2(f2_pack(c0.z, c1.z), f2_pack(-c0.w, -c1.w));
+      }
+    }
+    __syncthreads();
+
+    for (long u = u0 + warp; u < round_end; u += TPR_WARPS) {
+      const int b = (int)(u / upc);
+      const int m = (int)(u - (long)b * upc) * 32 + lane;      // this thread's query point
+      const long row = (long)b * N + m;
+      unsigned char* base = smem + (size_t)(b - b0) * tpr_cloud_bytes(N);
+      const ulonglong2* pxy = reinterpret_cast<const ulonglong2*>(base);
+      const ulonglong2* pzw = pxy + npad / 2;
+      const float4* packed = reinterpret_cast<const float4*>(pzw + npad / 2);
+      const float4 q = packed[m];
+      bool slow = (p.force_slow != 0);
+
+#if L3D_TPR_STOP == 1
+      if (q.x == 12345.f) reinterpret_cast<long long*>(p.out_idx)[row * k] = 1;
+      continue;
+#endif
+      if (!p.force_slow) {
+        const unsigned long long qx2 = f2_pack(q.x, q.x), qy2 = f2_pack(q.y, q.y), qz2 = f2_pack(q.z, q.z);
+        const unsigned long long two2 = f2_pack(2.0f, 2.0f);
+        // ---- pass 1: group maxima of s = 2 q.c - |c|^2 (the key without its final "- |q|^2": monotone) ----
+        // s of eight candidate pairs, written stage by stage: sixteen independent fma chains in flight
+        auto eval8 = [&](const ulonglong2 (&cx)[8], const ulonglong2 (&cz)[8], unsigned long long (&t)[8], bool fused,
+                         unsigned long long h2v) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = fused ? f2_fma(qx2, cx[i].x, h2v) : f2_mul(qx2, cx[i].x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = f2_fma(qy2, cx[i].y, t[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = f2_fma(qz2, cz[i].x, t[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = f2_fma(two2, t[i], cz[i].y);
+        };
+        auto load8 = [&](int o, ulonglong2 (&cx)[8], ulonglong2 (&cz)[8]) {      // candidate pairs 8 o .. 8 o + 7
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { cx[i] = pxy[o * 8 + i]; cz[i] = pzw[o * 8 + i]; }
+        };
+        if constexpr (PPG == 8) {
+          // N = 1024: a group is eight pairs.  Software-pipelined by hand — the operands of group g + 1 are loaded
+          // before group g is evaluated (ptxas does not overlap the trips of this loop by itself; the first ncu
+          // capture showed the warp waiting on its own LDS / fma latencies 60 % of the time with 2 warps per scheduler)
+          ulonglong2 ax[8], az[8], bx[8], bz[8];
+          load8(0, ax, az);
+#pragma unroll 1
+          for (int g = 0; g < TPR_G; g += 2) {
+            unsigned long long t[8];
+            float s0, s1, m0 = -INFINITY, m1 = -INFINITY;
+            load8(g + 1, bx, bz);
+            eval8(ax, az, t, false, 0ull);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              f2_unpack(t[i], s0, s1);     m0 = fmaxf(fmaxf(m0, s0), s1);
+              f2_unpack(t[i + 1], s0, s1); m1 = fmaxf(fmaxf(m1, s0), s1);
+            }
+            gmax[g * TPR_THREADS] = fmaxf(m0, m1);
+            load8(min(g + 2, TPR_G - 1), ax, az);
+            eval8(bx, bz, t, false, 0ull);
+            m0 = -INFINITY; m1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              f2_unpack(t[i], s0, s1);     m0 = fmaxf(fmaxf(m0, s0), s1);
+              f2_unpack(t[i + 1], s0, s1); m1 = fmaxf(fmaxf(m1, s0), s1);
+            }
+            gmax[(g + 1) * TPR_THREADS] = fmaxf(m0, m1);
+          }
+        } else {
+#pragma unroll 1
+          for (int g = 0; g < TPR_G; ++g) {
+            const ulonglong2* gxy = pxy + g * ppg;
+            const ulonglong2* gzw = pzw + g * ppg;
+            float mx = -INFINITY;
+#pragma unroll 4
+            for (int i = 0; i < ppg; ++i) {
+              const ulonglong2 cx = gxy[i], cz = gzw[i];
+              const unsigned long long dot = f2_fma(qz2, cz.x, f2_fma(qy2, cx.y, f2_mul(qx2, cx.x)));
+              float s0, s1;
+              f2_unpack(f2_fma(two2, dot, cz.y), s0, s1);
+              mx = fmaxf(fmaxf(mx, s0), s1);
+            }
+            gmax[g * TPR_THREADS] = mx;
+          }
+        }
+#if L3D_TPR_STOP == 2
+        { float acc = 0.f;
+          for (int i = 0; i < TPR_G; ++i) acc += gmax[i * TPR_THREADS];
+          reinterpret_cast<long long*>(p.out_idx)[row * k] = (long long)__float_as_int(acc); continue; }
+#endif
+        // ---- threshold: k-th largest of the 64 group maxima ----------------------------------------------
+        float t0;
+        {
+          float ga[32], gb[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { ga[i] = gmax[i * TPR_THREADS]; gb[i] = gmax[(32 + i) * TPR_THREADS]; }
+          reg_sort_desc<32>(ga);
+          reg_sort_desc<32>(gb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ga[i] = fmaxf(ga[i], gb[31 - i]);    // the 32 largest of the 64, bitonic
+          reg_merge_desc<32>(ga);
+          if (KT) {
+            t0 = ga[KT ? KT - 1 : 0];
+          } else {
+            t0 = ga[0];
+#pragma unroll
+            for (int i = 1; i < TPR_MAX_K; ++i) t0 = (i == k - 1) ? ga[i] : t0;
+          }
+        }
+        // s-space threshold (knn.cu row_threshold, DEFER): keeps every s whose key can reach the k-th group
+        // maximum's key kb, admits at most the few s within ~2 ulp below it
+        const float kb = __fsub_rn(t0, q.w);
+        float thr = __fadd_rd(__fadd_rd(kb, q.w), -__fmul_rn(fmaxf(fabsf(kb), 1e-30f), 1.1920929e-7f));
+#if L3D_TPR_FUSE_THR
+        // Pass 2 evaluates d = 2 (q.c - thr/2) - |c|^2 in ONE fma chain (the first product becomes an fma with the
+        // addend -thr/2), i.e. s - thr with different roundings: |d - (s - thr)| <= 7 eps (|q|^2 + 2 max|c|^2 + |thr|),
+        // eps = 2^-24 (three fma roundings of magnitude <= |q||c| + |thr|/2 <= (|q|^2 + |c|^2 + |thr|)/2, doubled, on
+        // either side, plus the final roundings).  Lowering thr by 20 eps (|q|^2 + max|c|^2 + |thr|) keeps every
+        // candidate with s >= thr on the non-negative side; the handful it admits besides are sorted out exactly below.
+        {
+          const float wm = __int_as_float(wmax[b - b0]);
+          const float delta = __fmul_ru(1.2e-6f, __fadd_ru(__fadd_ru(q.w, wm), fabsf(thr)));
+          thr = __fadd_rd(thr, -delta);
+        }
+        const float hthr = -0.5f * thr;
+        const unsigned long long h2 = f2_pack(hthr, hthr);
+#else
+        const unsigned long long nthr = f2_pack(-thr, -thr);
+#endif
+
+#if L3D_TPR_STOP == 3
+        { reinterpret_cast<long long*>(p.out_idx)[row * k] = (long long)__float_as_int(thr); continue; }
+#endif
+        // ---- pass 2: survivor mask per 32 candidates, set bits appended to the thread's index list -------
+        // The list is written through a running shared-memory address: every step stores its candidate index at the
+        // next free entry and only a step that really had a set bit advances the address (a dead step's store is
+        // overwritten by the next live one), so the steps carry no branches; the address saturates at entry TPR_CAP.
+        const uint32_t lbase = smem_u32(list);
+        const uint32_t lend = lbase + TPR_CAP * TPR_THREADS * 2;
+        uint32_t laddr = lbase;
+        auto take_lowest = [&](uint32_t& mk, int wbase) {
+          const uint32_t low = mk & (0u - mk);
+          uint32_t e;
+          asm("bfind.u32 %0, %1;" : "=r"(e) : "r"(low));                      // FLO of the isolated bit
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(laddr), "h"((unsigned short)(wbase + (int)e)) : "memory");
+          laddr = min(laddr + (low ? (uint32_t)(TPR_THREADS * 2) : 0u), lend);
+          mk ^= low;
+        };
+        uint32_t mk_prev = 0u;      // the mask of word w - 1 is unpacked while word w is evaluated (independent work)
+        // sign bits of the sixteen d = s - thr of eight pairs (set = below the threshold): bit 2 i = pair i's first
+        auto signs8 = [&](const unsigned long long (&t)[8]) -> uint32_t {
+          uint32_t n0 = 0u, n1 = 0u;            // two chains of eight funnel shifts
+#pragma unroll
+          for (int i = 3; i >= 0; --i) {
+            float d0, d1;
+            f2_unpack(t[i], d0, d1);
+            n0 = __funnelshift_l(__float_as_uint(d1), n0, 1);
+            n0 = __funnelshift_l(__float_as_uint(d0), n0, 1);
+            f2_unpack(t[4 + i], d0, d1);
+            n1 = __funnelshift_l(__float_as_uint(d1), n1, 1);
+            n1 = __funnelshift_l(__float_as_uint(d0), n1, 1);
+          }
+          return n0 + (n1 << 8);
+        };
+#if L3D_TPR_FUSE_THR
+        constexpr bool FUSED = true;
+        const unsigned long long hv = h2;
+#else
+        constexpr bool FUSED = false;
+        const unsigned long long hv = 0ull;
+#endif
+        {
+          const int noct = npad / 16;             // octets of candidate pairs; a mask word = two octets
+          ulonglong2 ax[8], az[8], bx[8], bz[8];
+          load8(0, ax, az);
+          load8(1, bx, bz);
+#pragma unroll 1
+          for (int w = 0; w < nwords; ++w) {
+            unsigned long long t[8];
+            eval8(ax, az, t, FUSED, hv);
+            load8(min(2 * w + 2, noct - 1), ax, az);
+#if !L3D_TPR_FUSE_THR
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = f2_add(t[i], nthr);
+#endif
+            const uint32_t lo16 = signs8(t);
+            eval8(bx, bz, t, FUSED, hv);
+            load8(min(2 * w + 3, noct - 1), bx, bz);
+#if !L3D_TPR_FUSE_THR
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = f2_add(t[i], nthr);
+#endif
+            const uint32_t hi16 = signs8(t);
+#if L3D_TPR_EXTRACT
+            // a word holds 0.7 survivors on average: three branch-free steps, then a rarely entered loop
+            take_lowest(mk_prev, (w - 1) * 32);
+            take_lowest(mk_prev, (w - 1) * 32);
+            take_lowest(mk_prev, (w - 1) * 32);
+#endif
+            while (mk_prev) take_lowest(mk_prev, (w - 1) * 32);
+            mk_prev = ~(lo16 + (hi16 << 16));
+          }
+        }
+        while (mk_prev) take_lowest(mk_prev, (nwords - 1) * 32);
+        const int cnt = (int)((laddr - lbase) / (TPR_THREADS * 2));
+        slow = cnt >= TPR_CAP;      // the saturated address means "TPR_CAP or more": those rows take the exactness net
+
+#if L3D_TPR_STOP == 4
+        { reinterpret_cast<long long*>(p.out_idx)[row * k] = (long long)cnt; continue; }
+#endif
+        // ---- final: composites of the first 32 survivors, in-register sort --------------------------------
+        unsigned long long a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool ok = i < cnt;
+          const uint32_t j = ok ? (uint32_t)list[i * TPR_THREADS] : 0u;
+          const unsigned long long c = tpr_composite(knn_key<MODE>(q, packed[j]), j);
+          a[i] = ok ? c : 0ull;
+        }
+        tpr_sort_desc<32>(a);
+        if (__any_sync(L3D_FULL_MASK, cnt > 32)) {
+          // survivors 32..63 of the rows that have them: sort, keep the better 32 of the union, clean up
+          unsigned long long bq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = (32 + i < cnt) && !slow;
+            const uint32_t j = ok ? (uint32_t)list[(32 + i) * TPR_THREADS] : 0u;
+            const unsigned long long c = tpr_composite(knn_key<MODE>(q, packed[j]), j);
+            bq[i] = ok ? c : 0ull;
+          }
+          tpr_sort_desc<32>(bq);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = (bq[31 - i] > a[i]) ? bq[31 - i] : a[i];
+          tpr_merge_desc<32>(a);
+        }
+
+        // ---- store the k best (indices ascending in rank): 128-bit stores when the row is 16-byte aligned --
+        if (!slow) {
+          if (p.idx64 == 1) {
+            long long* o = reinterpret_cast<long long*>(p.out_idx) + row * k;
+            if ((k & 1) == 0) {
+#pragma unroll
+              for (int pos = 0; pos < TPR_MAX_K; pos += 2)
+                if (pos < k)
+                  *reinterpret_cast<longlong2*>(o + pos) =
+                      make_longlong2((long long)tpr_comp_index(a[pos]), (long long)tpr_comp_index(a[pos + 1]));
+            } else {
+#pragma unroll
+              for (int pos = 0; pos < TPR_MAX_K; ++pos)
+                if (pos < k) o[pos] = (long long)tpr_comp_index(a[pos]);
+            }
+          } else {
+#pragma unroll
+            for (int pos = 0; pos < TPR_MAX_K; ++pos)
+              if (pos < k) knn_store_index(p, row * k + pos, tpr_comp_index(a[pos]));
+          }
+          if (p.out_val) {
+#pragma unroll
+            for (int pos = 0; pos < TPR_MAX_K; ++pos)
+              if (pos < k) p.out_val[row * k + pos] = knn_val_xform(tpr_comp_key(a[pos]), p.val_xform);
+          }
+        }
+      }
+
+      // ---- exactness net: rows with more than 64 survivors (duplicate points, clouds far from the origin whose
+      // keys collapse onto a few fp32 values) are redone by the warp-cooperative routine of knn.cu (lane-maximum
+      // threshold, shuffle networks; itself backed by the exact k-round scan); the testing hook goes there too ----
+      unsigned todo = __ballot_sync(L3D_FULL_MASK, slow);
+      while (todo) {
+        const int from = __ffs(todo) - 1;
+        todo &= todo - 1;
+        float4 qs;
+        qs.x = __shfl_sync(L3D_FULL_MASK, q.x, from); qs.y = __shfl_sync(L3D_FULL_MASK, q.y, from);
+        qs.z = __shfl_sync(L3D_FULL_MASK, q.z, from); qs.w = __shfl_sync(L3D_FULL_MASK, q.w, from);
+        knn_row_v2<MODE>(p, packed, cbuf, qs, row - lane + from, ntile / KNN_TILE, lane);
+        __syncwarp();
+      }
+
+      if (FEAT) {
+        // get_graph_feature() fused (model_common_utils.py:132-155): cat(x[nbr], x[centre]) for the 32 rows of this
+        // warp; their 32*k (index, position) entries are one contiguous run per channel -> coalesced stores
+        __syncwarp();
+        const long e0 = (row - lane) * k;                          // first entry of the warp's rows
+        const size_t cs = (size_t)N * k;
+        const int n0 = m - lane;
+        float* f = p.feat_out + (size_t)b * 6 * cs + (size_t)n0 * k;
+        for (int e = lane; e < 32 * k; e += 32) {
+          const int j = (int)reinterpret_cast<const volatile long long*>(p.out_idx)[e0 + e];
+          const float4 c = packed[j];
+          const float4 ctr = packed[n0 + e / k];
+          f[e] = c.x; f[cs + e] = c.y; f[2 * cs + e] = c.z;
+          f[3 * cs + e] = ctr.x; f[4 * cs + e] = ctr.y; f[5 * cs + e] = ctr.z;
+        }
+      }
+    }
+    u0 = round_end;
+    __syncthreads();   // every warp is done with the resident clouds before the next round overwrites them
+  }
+}
+
+static thread_local int g_knn_path = 0;   // 0 auto, 1 warp-per-row-pair kernel only, 2 thread-per-row whenever eligible
+int knn_path_flag() { return g_knn_path; }
+
+static int tpr_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// shapes the thread-per-row kernel takes at all (the launcher in knn.cu adds the "enough rows" rule)
+bool knn_tpr_eligible(const KnnParams& p) {
+  if (p.N % 32 != 0 || p.N < TPR_MIN_N || p.N > TPR_MAX_N || p.k > TPR_MAX_K || p.k < 1) return false;
+  if (p.M != p.N || p.query != nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(p.cand) & 7u) != 0) return false;       // float2 staging loads
+  if (p.idx64 == 1 && (reinterpret_cast<uintptr_t>(p.out_idx) & 15u) != 0) return false;
+  if (p.feat_out && p.idx64 != 1) return false;
+  return tpr_smem_bytes(p.N) <= KNN_SMEM_LIMIT;
+}
+
+template <int PPG, int KT, bool FEAT>
+static int tpr_launch_t(const KnnParams& p, cudaStream_t stream) {
+  auto kern = knn_tpr_kernel<PPG, KT, FEAT>;
+  const size_t smem = tpr_smem_bytes(p.N);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    // per-(device, function) attribute shared by every host thread: raise it once to the architectural maximum
+    static std::mutex mu;
+    static uint64_t done_mask = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 64 || !(done_mask >> dev & 1)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM_LIMIT);
+      if (e != cudaSuccess) return (int)e;
+      if (dev < 64) done_mask |= (uint64_t)1 << dev;
+    }
+  }
+  const long units = (long)p.B * (p.N / 32);
+  long grid = tpr_sm_count();                      // one CTA per SM, every CTA resident at once
+  if (grid > units) grid = units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TPR_THREADS);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess) return (int)le;
+  count_launch();
+  L3D_LAUNCH_CHECK();
+  return L3D_OK;
+}
+
+int knn_tpr_launch(const KnnParams& p, cudaStream_t stream) {
+  const bool n1024 = ((p.N + 127) & ~127) == 1024;
+  if (p.feat_out) {
+    if (n1024 && p.k == 20) return tpr_launch_t<8, 20, true>(p, stream);
+    return tpr_launch_t<0, 0, true>(p, stream);
+  }
+  if (n1024 && p.k == 20) return tpr_launch_t<8, 20, false>(p, stream);
+  return tpr_launch_t<0, 0, false>(p, stream);
+}
+
+}  // namespace l3d
+
+extern "C" void l3d_debug_knn_path(int path) { l3d::g_knn_path = (path == 1 || path == 2) ? path : 0; }
