@@ -310,11 +310,12 @@ def run_ours(args, rank, local_rank, world):
                              % (pool, pool * (in_bytes + out_bytes) / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "peak_source": peak_src, "kernel": "l3d::knn_kernel<EXPANSION_NEG,KS=1>",
+                         "peak_source": peak_src, "kernel": "l3d::knn_duo_kernel<PPG=8,k=20> (knn_tpr.cu: thread-per-row selection, two warps per 64 rows)",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "fp32_gflops_achieved": B * N * N * FLOP_PER_PAIR / kernel_s / 1e9,
                          "note": "fp32-issue/selection bound once the NxN matrix is not materialised "
-                                 "(SURVEY.md §8d): a perfect kernel reaches ~20% of HBM peak at this shape"},
+                                 "(SURVEY.md §8d): a perfect kernel reaches ~20% of HBM peak at this shape; the fma "
+                                 "floor of the two candidate passes is 8.3 us (DESIGN.md §3.1)"},
             "e2e": {"value": world * B * N * N * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * N * k * 2,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps,

@@ -48,7 +48,7 @@ uint64_t l3d_launch_count(void);
  * (normally taken only when a row overflows the candidate buffer, e.g. duplicate points). */
 void l3d_debug_force_slow_path(int on);
 /* Testing hook (per host thread): which kernel knn() on xyz clouds takes when both apply.  0 = automatic (the
- * thread-per-row kernel of knn_tpr.cu when k <= 24, N % 32 == 0, 128 <= N <= 2048 and B*N/32 >= 592, else the
+ * thread-per-row kernel of knn_tpr.cu when k <= 24, N % 32 == 0, 128 <= N <= 2048 and B*N/32 >= 512, else the
  * warp-per-row-pair kernel of knn.cu), 1 = never the thread-per-row kernel, 2 = the thread-per-row kernel whenever
  * the shape is eligible, whatever the batch size.  Both kernels return bit-identical results. */
 void l3d_debug_knn_path(int path);

@@ -61,7 +61,7 @@ constexpr int KNN_CHUNK = 1024;  // points per bulk-copy staging chunk
 #define L3D_KNN_BOUNDS __launch_bounds__(KNN_THREADS)
 #endif
 #ifndef L3D_KNN_TPR_MIN_UNITS
-#define L3D_KNN_TPR_MIN_UNITS 592   // 32-row warp units below which knn() stays on the warp-per-row-pair kernel (4 per SM)
+#define L3D_KNN_TPR_MIN_UNITS 512   // 32-row units below which knn() stays on the warp-per-row-pair kernel (measured tie at 512: profiles/r02/knn_paths_time.txt)
 #endif
 constexpr int TPR_K_MAX = 24;
 constexpr int KNN_R = L3D_KNN_R;  // query rows per warp on the k <= 24 path (tuned in profiles/r01)
