@@ -10,6 +10,12 @@
 #include <thread>
 #include <cstdlib>
 #include <mutex>
+#include <condition_variable>
+#include <vector>
+#include <climits>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace l3d {
 static std::atomic<uint64_t> g_launches{0};
@@ -41,6 +47,84 @@ struct HostCtx {
   }
 };
 static HostCtx g_host;
+
+// Widening workers of l3d_knn_expansion_host.  An OpenMP parallel region per chunk costs a fork / join (~10 us) every
+// time, which caps the useful thread count at 4 and leaves the call bound by the 10.5 MB of int64 the host has to write
+// (profiles/r02/knn_host_path_sweep.txt).  These threads sleep on a condition variable between calls, are woken when a
+// call starts (the wake-up overlaps the H2D copy and the kernel), spin on the `ready` counter while the copies land and
+// each widen a fixed share of every chunk.  The calling thread is worker 0.
+struct WidenPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t gen = 0;                 // bumped once per call, under mu
+  int nworkers = 1;                 // including the caller
+  std::vector<std::thread> threads;
+  // the job of the current call (written before gen is bumped)
+  const unsigned short* src = nullptr;
+  int64_t* dst = nullptr;
+  long cuts[65] = {0};
+  int ncuts = 0;
+  std::atomic<int> ready{0};        // chunks whose copy has landed
+  std::atomic<int> done{0};         // helper threads that have finished the current job
+  std::atomic<int> abort{0};
+
+  static void relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+  }
+  void widen_share(int c, int w) {
+    const long i0 = cuts[c], i1 = cuts[c + 1], n = i1 - i0;
+    const long a = i0 + n * w / nworkers, z = i0 + n * (w + 1) / nworkers;
+    const unsigned short* s = src;
+    int64_t* d = dst;
+    for (long t = a; t < z; ++t) d[t] = (int64_t)s[t];
+  }
+  void run_job(int w) {
+    for (int c = 0; c < ncuts; ++c) {
+      while (ready.load(std::memory_order_acquire) <= c) relax();
+      if (abort.load(std::memory_order_relaxed)) break;
+      widen_share(c, w);
+    }
+  }
+  void helper(int w) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+      }
+      run_job(w);
+      done.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void start(int n) {               // once, under g_host.mu
+    nworkers = n < 1 ? 1 : n;
+    for (int w = 1; w < nworkers; ++w) {
+      threads.emplace_back([this, w] { helper(w); });
+      threads.back().detach();      // they live as long as the process; the pool itself is never destroyed
+    }
+  }
+  void begin() {                    // job fields are set: wake the helpers
+    ready.store(0, std::memory_order_relaxed);
+    done.store(0, std::memory_order_relaxed);
+    abort.store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      ++gen;
+    }
+    cv.notify_all();
+  }
+  void finish(bool failed) {        // caller: release everything on failure, then wait for the helpers
+    if (failed) {
+      abort.store(1, std::memory_order_relaxed);
+      ready.store(INT_MAX, std::memory_order_release);
+    }
+    while (done.load(std::memory_order_acquire) < nworkers - 1) relax();
+  }
+};
+static WidenPool* g_pool = nullptr;
 }  // namespace l3d
 
 extern "C" int l3d_abi_version(void) { return 1; }
@@ -100,15 +184,41 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
     e = cudaStreamCreateWithFlags(&l3d::g_host.stream2, cudaStreamNonBlocking);
     if (e) return (int)e;
   }
-  constexpr int MAX_SLICES = 8;
-  static cudaEvent_t ev[MAX_SLICES] = {};
+  // Work plan: `nslice` kernel slices (clouds are independent) on two streams, each slice's indices returned in
+  // `nchunk` device-to-host copies with an event after every copy, so the host widens chunk c while later chunks are
+  // still on the bus or still being computed (profiles/r02/knn_host_path_sweep.txt has the sweeps of both knobs).
+  constexpr int MAX_SLICES = 8, MAX_CHUNKS = 8;
+  static cudaEvent_t ev[MAX_SLICES * MAX_CHUNKS] = {};
   cudaStream_t st[2] = {l3d::g_host.stream, l3d::g_host.stream2};
-  static int slice_cap = 0;
+  static int slice_cap = 0, chunk_cfg = 0, nthreads = 0, use_pool = 1;
   if (slice_cap == 0) {
     const char* ev_s = getenv("L3D_HOST_SLICES");
-    slice_cap = ev_s ? atoi(ev_s) : 2;     // measured at C2 (profiles/r02): 1 / 2 / 4 / 8 slices = 130 / 104 / 118 / 157 us
+    slice_cap = ev_s ? atoi(ev_s) : 2;
     if (slice_cap < 1) slice_cap = 1;
     if (slice_cap > MAX_SLICES) slice_cap = MAX_SLICES;
+    const char* ev_c = getenv("L3D_HOST_D2H_CHUNKS");
+    chunk_cfg = ev_c ? atoi(ev_c) : 1;
+    if (chunk_cfg < 1) chunk_cfg = 1;
+    if (chunk_cfg > MAX_CHUNKS) chunk_cfg = MAX_CHUNKS;
+    const char* ev_p = getenv("L3D_HOST_POOL");
+    use_pool = ev_p ? atoi(ev_p) : 1;
+    const char* ev_t = getenv("L3D_HOST_THREADS");
+    // measured at C2 (profiles/r02/knn_host_path_sweep.txt): OpenMP 4 threads 108.7 us; pool 4 / 8 / 16 threads
+    // 109.4 / 94.6 / 89.1 us.  The helpers spin while a call is in flight, so the default leaves half of the machine
+    // to the other ranks of a node (torchrun exports LOCAL_WORLD_SIZE; OMP_NUM_THREADS = 1 there is NOT a clamp here).
+    const int hw = (int)std::thread::hardware_concurrency();
+    const char* ev_w = getenv("LOCAL_WORLD_SIZE");
+    const int lws = (ev_w && atoi(ev_w) > 0) ? atoi(ev_w) : 1;
+    int dflt = use_pool ? 16 : 4;
+    if (use_pool && hw > 0 && dflt > hw / (2 * lws)) dflt = hw / (2 * lws) < 4 ? 4 : hw / (2 * lws);
+    nthreads = ev_t ? atoi(ev_t) : dflt;
+    if (nthreads < 1) nthreads = 1;
+    if (hw > 0 && nthreads > hw) nthreads = hw;
+    if (nthreads > 32) nthreads = 32;
+    if (use_pool) {
+      l3d::g_pool = new l3d::WidenPool();
+      l3d::g_pool->start(nthreads);
+    }
   }
   int nslice = B >= 16 ? 8 : (B >= 8 ? 4 : (B >= 2 ? 2 : 1));
   if (nslice > slice_cap) nslice = slice_cap;
@@ -116,43 +226,67 @@ extern "C" int l3d_knn_expansion_host(const float* x_host, int B, int N, int k, 
   unsigned short* dout = (unsigned short*)l3d::g_host.out;
   int bounds[MAX_SLICES + 1];
   for (int i = 0; i <= nslice; ++i) bounds[i] = (int)((long)B * i / nslice);
+  // copy plan first (it depends on sizes only), so that the widening workers can be woken before any CUDA call
+  long cuts[MAX_SLICES * MAX_CHUNKS + 1];
+  int chunks_of[MAX_SLICES];
+  int ncuts = 0;
+  cuts[0] = 0;
   for (int i = 0; i < nslice; ++i) {
+    const long cnt = (long)(bounds[i + 1] - bounds[i]) * N * k, oo = (long)bounds[i] * N * k;
+    chunks_of[i] = (cnt >= (long)chunk_cfg * 65536) ? chunk_cfg : 1;      // small outputs: one copy
+    for (int c = 0; c < chunks_of[i]; ++c) cuts[++ncuts] = oo + cnt * (c + 1) / chunks_of[i];
+  }
+  l3d::WidenPool* pool = use_pool ? l3d::g_pool : nullptr;
+  if (pool) {
+    pool->src = stage; pool->dst = idx_host; pool->ncuts = ncuts;
+    for (int i = 0; i <= ncuts; ++i) pool->cuts[i] = cuts[i];
+    pool->begin();
+  }
+  int fail = 0;
+  int cut = 0;
+  for (int i = 0; i < nslice && !fail; ++i) {
     const int b0 = bounds[i], nb = bounds[i + 1] - b0;
-    if (!ev[i]) { e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e) return (int)e; }
     cudaStream_t s = st[i & 1];
-    const size_t io = (size_t)b0 * 3 * N, oo = (size_t)b0 * N * k;
+    const size_t io = (size_t)b0 * 3 * N;
     if (nb > 0) {
       e = cudaMemcpyAsync((void*)(din + io), x_host + io, (size_t)nb * 3 * N * sizeof(float), cudaMemcpyHostToDevice, s);
-      if (e) return (int)e;
-      rc = l3d::knn_expansion_u16(din + io, nb, N, k, dout + oo, s);
-      if (rc) return rc;
-      e = cudaMemcpyAsync(stage + oo, dout + oo, (size_t)nb * N * k * sizeof(unsigned short), cudaMemcpyDeviceToHost, s);
-      if (e) return (int)e;
+      if (e) { fail = (int)e; break; }
+      rc = l3d::knn_expansion_u16(din + io, nb, N, k, dout + (size_t)b0 * N * k, s);
+      if (rc) { fail = rc; break; }
     }
-    e = cudaEventRecord(ev[i], s);
-    if (e) return (int)e;
+    for (int c = 0; c < chunks_of[i]; ++c, ++cut) {
+      const long c0 = cuts[cut], c1 = cuts[cut + 1];
+      if (c1 > c0) {
+        e = cudaMemcpyAsync(stage + c0, dout + c0, (size_t)(c1 - c0) * sizeof(unsigned short), cudaMemcpyDeviceToHost, s);
+        if (e) { fail = (int)e; break; }
+      }
+      if (!ev[cut]) { e = cudaEventCreateWithFlags(&ev[cut], cudaEventDisableTiming); if (e) { fail = (int)e; break; } }
+      e = cudaEventRecord(ev[cut], s);
+      if (e) { fail = (int)e; break; }
+    }
   }
-  // widen slice by slice as the copies land
-  static int nthreads = 0;
-  if (nthreads == 0) {
-    const char* ev_t = getenv("L3D_HOST_THREADS");
-    nthreads = ev_t ? atoi(ev_t) : 4;      // 1 / 2 / 4 / 8 / 16 threads at 8 slices: 253 / 190 / 158 / 159 / 157 us
-    if (nthreads < 1) nthreads = 1;
-    // NOT clamped by omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, and the num_threads
-    // clause below is allowed to exceed that default; clamp by the machine instead
-    const int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 0 && nthreads > hw) nthreads = hw;
-  }
-  for (int i = 0; i < nslice; ++i) {
+  // widen chunk by chunk as the copies land
+  for (int i = 0; i < ncuts && !fail; ++i) {
     e = cudaEventSynchronize(ev[i]);
-    if (e) return (int)e;
-    const long i0 = (long)bounds[i] * N * k, i1 = (long)bounds[i + 1] * N * k;
-    const unsigned short* src = stage;
+    if (e) { fail = (int)e; break; }
+    if (pool) {
+      pool->ready.store(i + 1, std::memory_order_release);
+      pool->widen_share(i, 0);
+    } else {
+      const long i0 = cuts[i], i1 = cuts[i + 1];
+      const unsigned short* src = stage;
 #pragma omp parallel for schedule(static) num_threads(nthreads)
-    for (long c = i0 / 4096; c < (i1 + 4095) / 4096; ++c) {
-      const long a = c * 4096 < i0 ? i0 : c * 4096, z = (c + 1) * 4096 > i1 ? i1 : (c + 1) * 4096;
-      for (long t = a; t < z; ++t) idx_host[t] = (int64_t)src[t];
+      for (long c = i0 / 4096; c < (i1 + 4095) / 4096; ++c) {
+        const long a = c * 4096 < i0 ? i0 : c * 4096, z = (c + 1) * 4096 > i1 ? i1 : (c + 1) * 4096;
+        for (long t = a; t < z; ++t) idx_host[t] = (int64_t)src[t];
+      }
     }
+  }
+  if (pool) pool->finish(fail != 0);
+  if (fail) {
+    cudaStreamSynchronize(st[0]);
+    cudaStreamSynchronize(st[1]);
+    return fail;
   }
   return L3D_OK;
 }
