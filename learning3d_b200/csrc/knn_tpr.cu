@@ -486,6 +486,13 @@ __global__ void __launch_bounds__(tpr_threads(R), 1) knn_tpr_kernel(const KnnPar
 // owns row 32 h + lane.  The halves meet in shared memory (group maxima, thresholds, two index sub-lists per row),
 // the phases are separated by a 64-thread named barrier.  Rows per SM, warps per SM and fma work are unchanged;
 // shared-memory operand traffic halves.
+#ifndef L3D_DUO_UNROLL_G
+#define L3D_DUO_UNROLL_G 1   // candidate groups per pass-1 loop trip
+#endif
+#ifndef L3D_DUO_UNROLL_W
+#define L3D_DUO_UNROLL_W 1   // mask words per pass-2 loop trip
+#endif
+constexpr int DUO_UNROLL_G = L3D_DUO_UNROLL_G, DUO_UNROLL_W = L3D_DUO_UNROLL_W;
 constexpr int DUO_THREADS = 256, DUO_PER_CTA = DUO_THREADS / 64;
 constexpr int DUO_LCAP = 32;                 // entries per (row, candidate half) sub-list that count as "not full"
 constexpr int DUO_LROWS = DUO_LCAP + 4;      // + the entries the three unclamped steps of a word may touch
@@ -530,30 +537,48 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) knn_duo_kernel(const KnnParams
     const long round_end = min(u1, (long)(b0 + tpr_slots(N)) * upc);
     const int nb = (int)((round_end - 1) / upc) - b0 + 1;
 
-    // ---- stage the clouds of this round (as knn_tpr_kernel) ------------------------------------------------
+    // ---- stage the clouds of this round: pair layout for the packed loops + float4 for the gathers --------------
+    // Four candidate pairs per thread and trip, all twelve global loads issued before the first use (indices
+    // clamped instead of predicated): the loop used to pay one L2 round trip per trip (~3 of the 26.6 us per launch).
     if (tid < 2) wmax[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < nb * (ntile / 2); i += THREADS) {
-      const int s = i / (ntile / 2), pi = i - s * (ntile / 2);
-      unsigned char* base = smem + (size_t)s * tpr_cloud_bytes(N);
-      ulonglong2* pxy = reinterpret_cast<ulonglong2*>(base);
-      ulonglong2* pzw = pxy + npad / 2;
-      float4* packed = reinterpret_cast<float4*>(pzw + npad / 2);
-      const float* src = p.cand + (size_t)(b0 + s) * 3 * N;
-      float4 c0 = knn_padding<MODE>(), c1 = knn_padding<MODE>();
-      if (2 * pi < N) {
-        const float2 x = *reinterpret_cast<const float2*>(src + 2 * pi);
-        const float2 y = *reinterpret_cast<const float2*>(src + N + 2 * pi);
-        const float2 z = *reinterpret_cast<const float2*>(src + 2 * (size_t)N + 2 * pi);
-        c0 = knn_pack<MODE>(x.x, y.x, z.x);
-        c1 = knn_pack<MODE>(x.y, y.y, z.y);
-        atomicMax(&wmax[s], __float_as_int(fmaxf(c0.w, c1.w)));
-      }
-      packed[2 * pi] = c0;
-      packed[2 * pi + 1] = c1;
-      if (2 * pi < npad) {
-        pxy[pi] = make_ulonglong2(f2_pack(c0.x, c1.x), f2_pack(c0.y, c1.y));
-        pzw[pi] = make_ulonglong2(f2_pack(c0.z, c1.z), f2_pack(-c0.w, -c1.w));
+    {
+      const int half = ntile / 2;                     // candidate pairs per resident cloud, tile padding included
+      const int total = nb * half;                    // nb <= 2
+      for (int i0 = tid; i0 < total; i0 += 4 * THREADS) {
+        float2 X[4], Y[4], Z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = min(i0 + u * THREADS, total - 1);
+          const int sc = (i >= half) ? 1 : 0, pi = min(i - sc * half, N / 2 - 1);
+          const float* src = p.cand + (size_t)(b0 + sc) * 3 * N;
+          X[u] = *reinterpret_cast<const float2*>(src + 2 * pi);
+          Y[u] = *reinterpret_cast<const float2*>(src + N + 2 * pi);
+          Z[u] = *reinterpret_cast<const float2*>(src + 2 * (size_t)N + 2 * pi);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * THREADS;
+          if (i < total) {
+            const int sc = (i >= half) ? 1 : 0, pi = i - sc * half;
+            unsigned char* base = smem + (size_t)sc * tpr_cloud_bytes(N);
+            ulonglong2* pxy = reinterpret_cast<ulonglong2*>(base);
+            ulonglong2* pzw = pxy + npad / 2;
+            float4* packed = reinterpret_cast<float4*>(pzw + npad / 2);
+            float4 c0 = knn_padding<MODE>(), c1 = knn_padding<MODE>();
+            if (2 * pi < N) {   // N is even: a pair is either real or padding
+              c0 = knn_pack<MODE>(X[u].x, Y[u].x, Z[u].x);
+              c1 = knn_pack<MODE>(X[u].y, Y[u].y, Z[u].y);
+              atomicMax(&wmax[sc], __float_as_int(fmaxf(c0.w, c1.w)));      // |c|^2 >= 0: integer order == float order
+            }
+            packed[2 * pi] = c0;
+            packed[2 * pi + 1] = c1;
+            if (2 * pi < npad) {
+              pxy[pi] = make_ulonglong2(f2_pack(c0.x, c1.x), f2_pack(c0.y, c1.y));
+              pzw[pi] = make_ulonglong2(f2_pack(c0.z, c1.z), f2_pack(-c0.w, -c1.w));
+            }
+          }
+        }
       }
     }
     __syncthreads();
@@ -580,7 +605,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) knn_duo_kernel(const KnnParams
         for (int r = 0; r < 2; ++r) { qx2[r] = f2_pack(q[r].x, q[r].x); qy2[r] = f2_pack(q[r].y, q[r].y); qz2[r] = f2_pack(q[r].z, q[r].z); }
         const unsigned long long two2 = f2_pack(2.0f, 2.0f);
         // ---- pass 1: maxima of this warp's 32 candidate groups, two rows per thread --------------------------
-#pragma unroll 1
+#pragma unroll DUO_UNROLL_G
         for (int gi = 0; gi < TPR_G / 2; ++gi) {
           const int g = h * (TPR_G / 2) + gi;
           const ulonglong2* gxy = pxy + g * ppg;
@@ -648,7 +673,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) knn_duo_kernel(const KnnParams
             mk ^= low;
           };
           const int w_begin = h * (nwords / 2), w_end = w_begin + nwords / 2;
-#pragma unroll 1
+#pragma unroll DUO_UNROLL_W
           for (int w = w_begin; w < w_end; ++w) {
             uint32_t m16[2][2];
 #pragma unroll

@@ -19,6 +19,9 @@ for v in "$@"; do
     g1)     build g1 -DL3D_TPR_UNROLL_G=1 & ;;
     g4)     build g4 -DL3D_TPR_UNROLL_G=4 & ;;
     loop)   build loop -DL3D_TPR_EXTRACT=0 & ;;
+    dg2)    build dg2 -DL3D_DUO_UNROLL_G=2 & ;;
+    dw2)    build dw2 -DL3D_DUO_UNROLL_W=2 & ;;
+    dg2w2)  build dg2w2 -DL3D_DUO_UNROLL_G=2 -DL3D_DUO_UNROLL_W=2 & ;;
     r1)     build r1 -DL3D_TPR_R=1 & ;;
     r1dsetp) build r1dsetp -DL3D_TPR_R=1 -DL3D_TPR_DSETP=1 & ;;
     stop[1-4]) build $v -DL3D_TPR_STOP=${v#stop} & ;;
