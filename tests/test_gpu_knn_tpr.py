@@ -138,3 +138,25 @@ def test_tpr_host_entry_point_c2(oracle_mod):
     _C.check(_C.lib().l3d_knn_expansion_host(x.ctypes.data_as(ctypes.c_void_p), 32, 1024, 20,
                                              out.ctypes.data_as(ctypes.c_void_p)))
     assert np.array_equal(out, oracle_mod.knn_expansion(x, 20, mt=True))
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_entry_point_repeated_calls_same_buffers(oracle_mod, pinned):
+    """Repeated l3d_knn_expansion_host calls on the same host buffers (pinned and pageable): new data in the same buffers
+    must give new results (the widening workers and the staging buffers are reused from call to call)."""
+    from learning3d_b200 import _C
+    import ctypes
+    rng = np.random.default_rng(17)
+    B, N, k = 32, 1024, 20
+    if pinned:
+        xt = torch.empty(B, 3, N).pin_memory()
+        ot = torch.empty(B, N, k, dtype=torch.int64).pin_memory()
+        x, out = xt.numpy(), ot.numpy()
+    else:
+        x, out = np.empty((B, 3, N), np.float32), np.empty((B, N, k), np.int64)
+    for rep in range(4):
+        x[...] = rng.random((B, 3, N), dtype=np.float32)
+        out[...] = -1
+        _C.check(_C.lib().l3d_knn_expansion_host(x.ctypes.data_as(ctypes.c_void_p), B, N, k,
+                                                 out.ctypes.data_as(ctypes.c_void_p)))
+        assert np.array_equal(out, oracle_mod.knn_expansion(x, k, mt=True)), "call %d" % rep
