@@ -8,23 +8,28 @@
 // is a chain of warp shuffles: ~64 SHFL + 65 ISETP + 48 SEL per row, issue slots 53 % busy, and neither fewer
 // arithmetic instructions (packed fp32) nor more resident warps moved the clock.  Here a THREAD owns a query
 // row and a warp owns 32 consecutive rows of one cloud:
-//   * every candidate operand is a shared-memory BROADCAST (all lanes read the same 16 bytes: one wavefront),
-//     two candidates per packed FFMA2 as before;
+//   * every candidate operand is a shared-memory BROADCAST, two candidates per packed FFMA2 as before;
 //   * the selection never leaves the thread's registers — no shuffles, no scans, no per-warp buffers:
 //       pass 1: the maxima of 64 candidate groups (one FMNMX3 per candidate pair);
-//       threshold: the k-th largest group maximum through an in-register bitonic network (2 x sort-32 +
-//         merge; FMNMX only) — at least k keys reach it and on average 23.5 do (never more than 32 in
-//         99.96 % of uniformly random rows);
-//       pass 2: the same packed expressions again (same bits), the sign of s - thr shifted into a 32-bit
-//         survivor mask per 32 candidates, the few set bits appended to a per-thread index list;
+//       threshold: the k-th largest group maximum through an in-register network (2 x merge-exchange sort-32,
+//         max-merge, pruned bitonic merge; FMNMX only) — at least k keys reach it and on average 23.5 do
+//         (never more than 32 in 99.96 % of uniformly random rows);
+//       pass 2: the same packed chain with -thr/2 folded into its first product (threshold lowered by a proven
+//         error bound), the sign of the result shifted into a 32-bit survivor mask per 32 candidates, the few set
+//         bits appended to a per-row list of 16-bit indices by branch-free steps;
 //       final: the <= 32 survivors are re-evaluated with the full key formula (one gathered LDS.128 each),
-//         packed into the 64-bit (key, ~index) composites of common.cuh and sorted by an in-register
-//         bitonic network; lanes store their k indices with 128-bit stores.
-//   * rows whose list exceeds 32 entries sort a second block of 32 and merge (whole warp, rare); beyond 64
-//     (duplicate points, adversarial ties) the row is redone by the exact k-round scan of knn_common.cuh.
+//         packed into 62-bit (key, ~index) composites that compare as positive doubles (DSETP, reg_sort.cuh) and
+//         sorted by a 191-exchange network; every thread stores its k indices with 128-bit stores.
+//   * rows whose list exceeds 32 entries sort a second block of 32 and merge (whole warp, rare); a full list
+//     (duplicate points, adversarial ties) hands the row to the warp-cooperative knn_row_v2 of knn_common.cuh
+//     (itself backed by the exact k-round scan).
+// Two kernels: knn_tpr_kernel (a warp = 32 rows over the whole candidate range; clouds with N % 64 != 0) and
+// knn_duo_kernel (two warps = 64 rows, each warp one candidate half for all 64 rows, so that every operand load
+// feeds two rows — the default; see its header below and profiles/micro/pipes.cu for the measurements behind it).
 // The price is parallelism: a row is a thread, so B*N/32 warps exist in total (1024 at C2 = 6.9 per SM) and
 // the kernel is one wave; the launcher therefore only takes this path when there are enough rows
-// (knn.cu: knn_launch), smaller batches stay on the warp-per-row-pair kernel.
+// (knn.cu: knn_launch, L3D_KNN_TPR_MIN_UNITS), smaller batches stay on the warp-per-row-pair kernel.
+// C2 (B=32, N=1024, k=20) on a B200: 33.1 us (knn.cu) -> 25.9 us (profiles/r02/knn_paths_time.txt).
 #include "knn_common.cuh"
 #include "reg_sort.cuh"
 #include "../../include/l3d_b200.h"
