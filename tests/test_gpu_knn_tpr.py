@@ -160,3 +160,15 @@ def test_host_entry_point_repeated_calls_same_buffers(oracle_mod, pinned):
         _C.check(_C.lib().l3d_knn_expansion_host(x.ctypes.data_as(ctypes.c_void_p), B, N, k,
                                                  out.ctypes.data_as(ctypes.c_void_p)))
         assert np.array_equal(out, oracle_mod.knn_expansion(x, k, mt=True)), "call %d" % rep
+
+
+@pytest.mark.parametrize("B,N,k", [
+    (40, 1024, 20),    # 640 duo units on 148 CTAs: some duos run two units (their shared arrays are reused)
+    (600, 128, 20),    # 1200 units of 64 rows, 2 per cloud: a CTA's range spans several rounds of resident clouds
+    (2, 256, 7),       # duo kernel, odd k (scalar index stores)
+    (3, 1088, 24),     # N % 64 == 0 but not a multiple of 128: padded groups in both candidate halves
+])
+def test_tpr_many_units_and_rounds(oracle_mod, B, N, k):
+    rng = np.random.default_rng(B * 7 + N)
+    x = rng.random((B, 3, N), dtype=np.float32)
+    assert np.array_equal(_knn(x, k, 2), oracle_mod.knn_expansion(x, k, mt=True))
