@@ -763,30 +763,36 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) knn_duo_kernel(const KnnParams
             for (int i = 0; i < 32; ++i) a[i] = (bq[31 - i] > a[i]) ? bq[31 - i] : a[i];
             tpr_merge_desc<32>(a);
           }
+          // ---- output: the warp's 32 rows are one contiguous block of 32 k indices.  Every thread drops its k
+          // indices as uint16 into a shared-memory image of that block (the duo's group-maximum array is free by
+          // now), then the warp writes the block with fully coalesced 128-bit stores; a row bound for the exactness
+          // net leaves garbage there, which that routine overwrites afterwards (same warp, program order).
+          unsigned short* ob = reinterpret_cast<unsigned short*>(gmax_d) + h * 1024;
           if (!slow) {
-            if (p.idx64 == 1) {
-              long long* o = reinterpret_cast<long long*>(p.out_idx) + row * k;
-              if ((k & 1) == 0) {
 #pragma unroll
-                for (int pos = 0; pos < TPR_MAX_K; pos += 2)
-                  if (pos < k)
-                    *reinterpret_cast<longlong2*>(o + pos) =
-                        make_longlong2((long long)tpr_comp_index(a[pos]), (long long)tpr_comp_index(a[pos + 1]));
-              } else {
-#pragma unroll
-                for (int pos = 0; pos < TPR_MAX_K; ++pos)
-                  if (pos < k) o[pos] = (long long)tpr_comp_index(a[pos]);
-              }
-            } else {
-#pragma unroll
-              for (int pos = 0; pos < TPR_MAX_K; ++pos)
-                if (pos < k) knn_store_index(p, row * k + pos, tpr_comp_index(a[pos]));
+            for (int pos = 0; pos < TPR_MAX_K; ++pos)
+              if (pos < k) ob[lane * k + pos] = (unsigned short)tpr_comp_index(a[pos]);
+          }
+          __syncwarp();
+          const long blk = (row0 + 32 * h) * k;                      // first entry of the warp's block
+          if (p.idx64 == 1) {
+            long long* o = reinterpret_cast<long long*>(p.out_idx) + blk;
+            for (int e2 = lane; e2 < 16 * k; e2 += 32) {             // pairs of indices
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(ob + 2 * e2);
+              *reinterpret_cast<longlong2*>(o + 2 * e2) = make_longlong2((long long)(w2 & 0xffffu), (long long)(w2 >> 16));
             }
-            if (p.out_val) {
+          } else if (p.idx64 == 2 && ((reinterpret_cast<uintptr_t>(p.out_idx) + (size_t)blk * 2) & 15u) == 0) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.out_idx) + blk);
+            for (int e8 = lane; e8 < 4 * k; e8 += 32) o[e8] = *reinterpret_cast<const uint4*>(ob + 8 * e8);
+          } else if (!slow) {
 #pragma unroll
-              for (int pos = 0; pos < TPR_MAX_K; ++pos)
-                if (pos < k) p.out_val[row * k + pos] = knn_val_xform(tpr_comp_key(a[pos]), p.val_xform);
-            }
+            for (int pos = 0; pos < TPR_MAX_K; ++pos)
+              if (pos < k) knn_store_index(p, row * k + pos, tpr_comp_index(a[pos]));
+          }
+          if (p.out_val && !slow) {
+#pragma unroll
+            for (int pos = 0; pos < TPR_MAX_K; ++pos)
+              if (pos < k) p.out_val[row * k + pos] = knn_val_xform(tpr_comp_key(a[pos]), p.val_xform);
           }
         }
       }
@@ -804,14 +810,18 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) knn_duo_kernel(const KnnParams
       }
 
       if (FEAT) {
-        // get_graph_feature() fused: cat(x[nbr], x[centre]) for this warp's 32 rows, coalesced per channel
+        // get_graph_feature() fused: cat(x[nbr], x[centre]) for this warp's 32 rows, coalesced per channel.  The
+        // indices come from the shared-memory image of the output block; a warp with a row that went through the
+        // exactness net (or the testing hook) re-reads what was stored.
         __syncwarp();
         const long e0 = (row0 + 32 * h) * k;
         const size_t cs = (size_t)N * k;
         const int n0 = m0 + 32 * h;
         float* f = p.feat_out + (size_t)b * 6 * cs + (size_t)n0 * k;
+        const bool from_smem = !__any_sync(L3D_FULL_MASK, slow);
+        const unsigned short* ob = reinterpret_cast<const unsigned short*>(gmax_d) + h * 1024;
         for (int e = lane; e < 32 * k; e += 32) {
-          const int j = (int)reinterpret_cast<const volatile long long*>(p.out_idx)[e0 + e];
+          const int j = from_smem ? (int)ob[e] : (int)reinterpret_cast<const volatile long long*>(p.out_idx)[e0 + e];
           const float4 c = packed[j];
           const float4 ctr = packed[n0 + e / k];
           f[e] = c.x; f[cs + e] = c.y; f[2 * cs + e] = c.z;
